@@ -1,0 +1,162 @@
+/*
+ * dlra.h — C ABI of libdlra.so, the B200-native engine for the per-step DLRA hot path of
+ * FHoltorf/LowRankIntegrators.jl.  The reference has no FFI: its seam is Julia
+ * multiple dispatch on  alg_cache(prob, alg, u, dt) / step!(integrator, alg, dt)
+ * (src/integrators/projector_splitting.jl:43,87,191-211; unconventional.jl:39,86,159-164;
+ * rank_adaptive_unconventional.jl:47,106,171-180).  Each entry point below names the reference
+ * code it replaces; julia/DLRAB200.jl binds them with `ccall`, and
+ * lowrankintegrators.jl_b200/_lib.py binds the same symbols with ctypes.
+ *
+ * Conventions: all matrices are fp64, column-major (Julia layout) with an explicit leading
+ * dimension in elements; pointers are DEVICE pointers unless the function name ends in `_host`;
+ * every call returns 0 on success or a DLRA_E* code, with the text in dlra_last_error();
+ * work is enqueued on the engine's own CUDA stream and is asynchronous unless stated;
+ * one caller thread per handle (the reference is single-task), handles are independent.
+ * One handle drives ONE GPU; multi-GPU runs use one process (handle) per GPU with the matrix
+ * rows (n) sharded in contiguous blocks, joined by dlra_comm_init (NCCL over NVLink).
+ */
+#ifndef DLRA_H_
+#define DLRA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dlra_engine* dlra_handle;
+
+enum {
+    DLRA_OK = 0,
+    DLRA_EINVAL = 1,     /* bad argument (the reference would throw MethodError / AssertionError) */
+    DLRA_ECUDA = 2,      /* CUDA runtime / driver failure */
+    DLRA_ENCCL = 3,      /* NCCL failure or NCCL not loadable */
+    DLRA_ESTATE = 4,     /* call sequence error (e.g. step without pushed data / without rhs) */
+    DLRA_ENOMEM = 5,
+    DLRA_EUNSUPPORTED = 6
+};
+
+/* dlra_create flags */
+enum {
+    DLRA_RANK_ADAPTIVE = 1,  /* size workspaces for the augmented 2r bases of the rank-adaptive integrator */
+    DLRA_FORCE_GENERIC = 2   /* debugging: use the generic (non-TMA, non-DMMA) contraction kernels only */
+};
+
+/* KSL orders: PrimalLieTrotter / DualLieTrotter / Strang (projector_splitting.jl:1-3) */
+enum { DLRA_KSL_PRIMAL = 0, DLRA_KSL_DUAL = 1, DLRA_KSL_STRANG = 2 };
+
+/* kinds of pushed data (src/integrators/data_integrator.jl:22-28 + the ΔA formation at
+ * projector_splitting.jl:119-121 and twins) */
+enum {
+    DLRA_DATA_SNAPSHOT = 0, /* A(t+dt); the engine forms ΔA = A(t+dt) − A(t) on the fly and then yprev ← ycurr */
+    DLRA_DATA_DELTA = 1     /* a pre-differenced increment ΔA */
+};
+
+/* sub-flow selectors and explicit RK sub-steppers standing in for K_alg/S_alg/L_alg
+ * (projector_splitting.jl:36-38, unconventional.jl:16-18, rank_adaptive_unconventional.jl:18-20) */
+enum { DLRA_FLOW_K = 0, DLRA_FLOW_S = 1, DLRA_FLOW_L = 2 };
+enum { DLRA_ODE_EULER = 0, DLRA_ODE_RK4 = 1, DLRA_ODE_TSIT5_FIXED = 2, DLRA_ODE_TSIT5 = 3 };
+
+/* operator storage for the device-evaluable right-hand sides */
+enum { DLRA_OP_NONE = 0, DLRA_OP_DENSE = 1, DLRA_OP_CSR = 2, DLRA_OP_IDENTITY_SCALED = 3 };
+
+typedef struct dlra_operator {
+    int kind;              /* DLRA_OP_* */
+    int64_t rows, cols;
+    const double* dense;   /* DENSE: rows x cols column-major, ld */
+    int64_t ld;
+    const int64_t* rowptr; /* CSR (0-based, rows+1 entries) */
+    const int32_t* colind;
+    const double* values;
+    double scale;          /* IDENTITY_SCALED: scale * I ; otherwise multiplies the operator */
+} dlra_operator;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+
+/* Replaces alg_cache(::MatrixDataProblem|::MatrixDEProblem, alg, u, dt) buffer allocation
+ * (projector_splitting.jl:43-105, unconventional.jl:39-107, rank_adaptive_unconventional.jl:47-131,
+ * and alg_recache :133-169 — workspaces are sized once for rmax, never reallocated per rank change).
+ * n_local: rows of this process' shard (== n on one GPU); m: columns; r0: initial rank; rmax: rank cap. */
+int dlra_create(int device, int64_t n_local, int64_t m, int r0, int rmax, int flags, dlra_handle* out);
+int dlra_destroy(dlra_handle h);
+const char* dlra_last_error(dlra_handle h); /* h may be NULL: last error of a failed dlra_create */
+const char* dlra_version(void);
+
+/* ---- multi-GPU (no counterpart in the single-process reference) ---------------- */
+int dlra_nccl_unique_id(void* id128);                       /* 128-byte ncclUniqueId, made on rank 0 */
+int dlra_comm_init(dlra_handle h, int nranks, int rank, const void* id128);
+/* caller-provided collectives (testing on CPU-less NCCL setups): not used in production */
+
+/* ---- factors: SVDLikeRepresentation(U,S,V) (LowRankArithmetic; README.md:85) ----------------- */
+/* deep copy in, as init() does with deepcopy(prob.u0) (projector_splitting.jl:110) */
+int dlra_set_factors_host(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds,
+                          const double* V, int64_t ldv, int r);
+int dlra_set_factors(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds,
+                     const double* V, int64_t ldv, int r);
+/* update_sol! (primitives.jl:82-90): deep copy out; synchronises the engine stream */
+int dlra_get_factors_host(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V,
+                          int64_t ldv, int* r);
+int dlra_get_factors(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V,
+                     int64_t ldv, int* r);
+int dlra_get_rank(dlra_handle h, int* r);
+/* borrow the engine's live factor buffers (valid until the next step; ld of U,V = n_local, m; ld of S = rmax cap) */
+int dlra_factor_ptrs(dlra_handle h, const double** U, int64_t* ldu, const double** S, int64_t* lds,
+                     const double** V, int64_t* ldv, int* r);
+
+/* ---- data feed: MatrixDataProblem (primitives.jl:23-30; data_integrator.jl:22-28) ------------- */
+/* yprev = y[1] | y(t0)   (projector_splitting.jl:91).  The *_host forms copy into engine-owned
+ * device buffers through a dedicated copy stream (overlaps the running step); the device forms
+ * BORROW the pointer: it must stay valid and unmodified until the step after the next push has run. */
+int dlra_data_init(dlra_handle h, const double* A0, int64_t ld);
+int dlra_data_init_host(dlra_handle h, const double* A0, int64_t ld);
+/* update_data!(ycurr, y, t, dt) for the NEXT step; kind = DLRA_DATA_SNAPSHOT | DLRA_DATA_DELTA */
+int dlra_data_push(dlra_handle h, const double* A, int64_t ld, int kind);
+int dlra_data_push_host(dlra_handle h, const double* A, int64_t ld, int kind);
+
+/* ---- right-hand sides: MatrixDEProblem (primitives.jl:13-17) in device-evaluable form ---------- */
+/* F(X,t) = A·X + X·Bᵀ + G·Hᵀ + c_had·(D1·X).*(D2·X)      (all terms optional)
+ * covers examples/generic_matrix.jl-style linear problems (W1·X + X + X·W2), Lyapunov-type
+ * A·X + X·Bᵀ (+ low-rank forcing) and the Burgers UQ right-hand side Δρ − (∇ρ).*ρ
+ * (test/data_agnostic_approximation.jl:31-33).  Replaces the default K_rhs/L_rhs/S_rhs closures
+ * (projector_splitting.jl:52-80, unconventional.jl:51-79, rank_adaptive_unconventional.jl:59-86).
+ * Operators are n x n (A, D1, D2) and m x m (B); G is n x q, H is m x q (device, column-major).
+ * With row sharding (dlra_comm_init) A, D1, D2, G take this rank's row block of the global operator
+ * (rows = n_local, cols = n_global).  Pointers are borrowed for the life of the handle. */
+int dlra_rhs_set(dlra_handle h, const dlra_operator* A, const dlra_operator* B, const double* G,
+                 int64_t ldg, const double* H, int64_t ldh, int q, const dlra_operator* D1,
+                 const dlra_operator* D2, double c_had);
+/* K_alg / S_alg / L_alg and their tolerances (Tsit5 defaults abstol=1e-6, reltol=1e-3) */
+int dlra_set_substepper(dlra_handle h, int flow, int ode, int nsub, double abstol, double reltol);
+
+/* ---- steps: one call == one reference step!(integrator, alg, dt) minus the t/iter bookkeeping -- */
+/* primal_LT_step! / dual_LT_step! / Strang (projector_splitting.jl:117-211).  For data problems
+ * the pushed ΔA is consumed; Strang on data needs two pushes, so call PRIMAL and DUAL with dt/2. */
+int dlra_step_ksl(dlra_handle h, int order, double t, double dt);
+/* unconventional_step! (unconventional.jl:121-164) */
+int dlra_step_bug(dlra_handle h, double t, double dt);
+/* rankadaptive_unconventional_step! + alg_recache (rank_adaptive_unconventional.jl:133-233).
+ * Synchronises (the new rank decides the next step's shapes). */
+int dlra_step_rabug(dlra_handle h, double t, double dt, double tol, int64_t rmax, int* r_new,
+                    int* rank_changed);
+/* greedy_step!(::SVDLikeRepresentation, ..., ::MatrixDataProblem) (greedy_integrator.jl:94-104):
+ * re-projection on the full pushed snapshot X (must be pushed as DLRA_DATA_SNAPSHOT). */
+int dlra_step_greedy(dlra_handle h, double t, double dt);
+
+int dlra_sync(dlra_handle h);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* ‖U·S·Vᵀ − Yref‖_F / ‖Yref‖_F without materialising n x m on the host (Yref: n_local x m device);
+ * with row sharding both norms are all-reduced.  Synchronises. */
+int dlra_reconstruct_error(dlra_handle h, const double* Yref, int64_t ld, double* rel_fro);
+/* dense reconstruction Y = U·S·Vᵀ into a device buffer (Matrix(u), LowRankArithmetic) */
+int dlra_reconstruct(dlra_handle h, double* Y, int64_t ld);
+/* number of kernels this handle launched so far / device ms of the dominant contraction kernel
+ * accumulated since the last reset (CUDA events on the engine stream) */
+int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass_launches, double* pass_ms_total,
+               double* pass_bytes_total, int reset);
+int dlra_set_profiling(dlra_handle h, int time_passes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLRA_H_ */

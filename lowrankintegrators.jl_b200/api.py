@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's Julia API for the DLRA hot path (Julia is not available in the build image, so
+the host side above the C ABI is Python; julia/DLRAB200.jl holds the `ccall` binding a maintainer would add).
+
+Same names, argument meaning and error behaviour as the reference:
+  MatrixDEProblem / MatrixDataProblem / DLRSolution / DLRIntegrator / solve      src/primitives.jl:13-104
+  ProjectorSplitting(PrimalLieTrotter|DualLieTrotter|Strang)                     src/integrators/projector_splitting.jl:1-41
+  UnconventionalAlgorithm                                                        src/integrators/unconventional.jl:13-21
+  RankAdaptiveUnconventionalAlgorithm(tol; rmax)                                 src/integrators/rank_adaptive_unconventional.jl:15-23
+  GreedyIntegrator (SVDLike data problems)                                       src/integrators/greedy_integrator.jl:16-22,94-104
+  SVDLikeRepresentation / TwoFactorRepresentation / truncated_svd                LowRankArithmetic (third party)
+Everything numeric in a step happens inside libdlra.so on the GPU; this file only sequences C-ABI calls.
+User right-hand sides are given in device-evaluable form (rhs.py) instead of Julia closures."""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import _lib as L
+from .engine import Engine, _is_torch
+
+# ------------------------------------------------------------------------------------------------
+# factor containers
+# ------------------------------------------------------------------------------------------------
+
+
+class SVDLikeRepresentation:
+    """u = U*S*V' (LowRankArithmetic.SVDLikeRepresentation): host copies of the factors."""
+
+    def __init__(self, U, S, V):
+        self.U = np.array(_host(U), dtype=np.float64, order="F")
+        self.S = np.array(_host(S), dtype=np.float64, order="F")
+        self.V = np.array(_host(V), dtype=np.float64, order="F")
+
+    def full(self):  # Matrix(u)
+        return self.U @ self.S @ self.V.T
+
+    @property
+    def rank(self):
+        return self.S.shape[0]
+
+    @property
+    def shape(self):
+        return (self.U.shape[0], self.V.shape[0])
+
+    def copy(self):
+        return SVDLikeRepresentation(self.U, self.S, self.V)
+
+
+class TwoFactorRepresentation:
+    """u = U*Z' (LowRankArithmetic.TwoFactorRepresentation)."""
+
+    def __init__(self, U, Z):
+        self.U = np.array(_host(U), dtype=np.float64, order="F")
+        self.Z = np.array(_host(Z), dtype=np.float64, order="F")
+
+    def full(self):
+        return self.U @ self.Z.T
+
+    @property
+    def rank(self):
+        return self.U.shape[1]
+
+    @property
+    def shape(self):
+        return (self.U.shape[0], self.Z.shape[0])
+
+
+def _host(x):
+    return x.detach().cpu().numpy() if _is_torch(x) else np.asarray(x)
+
+
+def truncate_to_tolerance(sigma, tol) -> int:
+    """LowRankArithmetic.truncate_to_tolerance; same (UNVERIFIED third-party) rule as csrc/jacobi.cuh."""
+    s, r = 0.0, len(sigma)
+    for sg in np.asarray(sigma)[::-1]:
+        s += float(sg) ** 2
+        if s > tol * tol:
+            break
+        r -= 1
+    return r
+
+
+def truncated_svd(A, r: Optional[int] = None, tol: Optional[float] = None) -> SVDLikeRepresentation:
+    """LowRankArithmetic.truncated_svd(A, r) / (A; tol): initial condition helper, host LAPACK like the reference
+    (outside the per-step hot path)."""
+    U, s, Vt = np.linalg.svd(np.asarray(_host(A), dtype=np.float64), full_matrices=False)
+    if r is None:
+        r = max(1, truncate_to_tolerance(s, tol))
+    return SVDLikeRepresentation(U[:, :r], np.diag(s[:r]), Vt[:r, :].T)
+
+
+# ------------------------------------------------------------------------------------------------
+# problems, solution, integrator  (src/primitives.jl)
+# ------------------------------------------------------------------------------------------------
+
+
+@dataclass
+class MatrixDEProblem:
+    f: object  # a device-evaluable right-hand side from rhs.py
+    u0: SVDLikeRepresentation
+    tspan: tuple
+
+
+class MatrixDataProblem:
+    def __init__(self, y, u0, tspan=None):
+        self.y = y
+        self.u0 = u0
+        self.tspan = (1, len(y)) if tspan is None else tspan  # primitives.jl:28-30
+
+
+@dataclass
+class DLRSolution:
+    Y: list
+    t: list
+
+
+class DLRIntegrator:
+    def __init__(self, engine, t, dt, sol, alg, probType, prob, save_everystep):
+        self.cache = engine  # the reference's alg cache == the engine's device workspaces
+        self.t, self.dt, self.sol, self.alg, self.probType, self.iter = t, dt, sol, alg, probType, 0
+        self.prob = prob
+        self.save_everystep = save_everystep
+
+    @property
+    def u(self):
+        return SVDLikeRepresentation(*self.cache.get_factors())
+
+
+def init_sol(dt, t0, tf, u0):  # primitives.jl:92-104
+    if isinstance(dt, (int, np.integer)) and not isinstance(dt, bool):
+        steps = list(range(t0, tf + 1, dt))
+        return DLRSolution([None] * len(steps), steps)
+    n = int(math.floor((tf - t0) / dt)) + 1
+    return DLRSolution([None] * n, list(np.linspace(t0, tf, n)))
+
+
+def update_sol(integ):  # primitives.jl:82-90
+    u = integ.u if integ.save_everystep else None
+    if integ.iter <= len(integ.sol.Y) - 1:
+        integ.sol.Y[integ.iter] = u
+        integ.sol.t[integ.iter] = integ.t
+    else:
+        integ.sol.Y.append(u)
+        integ.sol.t.append(integ.t)
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithms
+# ------------------------------------------------------------------------------------------------
+
+
+class PrimalLieTrotter:
+    pass
+
+
+class DualLieTrotter:
+    pass
+
+
+class Strang:
+    pass
+
+
+@dataclass
+class SubStepper:
+    """K_alg / S_alg / L_alg: 'tsit5' (adaptive, the reference default Tsit5()), 'tsit5_fixed', 'rk4', 'euler'."""
+    kind: str = "tsit5"
+    nsub: int = 1
+    abstol: float = 1e-6
+    reltol: float = 1e-3
+
+
+_ODE = {"euler": L.ODE_EULER, "rk4": L.ODE_RK4, "tsit5_fixed": L.ODE_TSIT5_FIXED, "tsit5": L.ODE_TSIT5}
+
+
+@dataclass
+class ProjectorSplitting:
+    order: object = field(default_factory=PrimalLieTrotter)
+    S_alg: Optional[SubStepper] = None
+    L_alg: Optional[SubStepper] = None
+    K_alg: Optional[SubStepper] = None
+
+
+@dataclass
+class UnconventionalAlgorithm:
+    S_alg: Optional[SubStepper] = None
+    L_alg: Optional[SubStepper] = None
+    K_alg: Optional[SubStepper] = None
+
+
+@dataclass
+class RankAdaptiveUnconventionalAlgorithm:
+    tol: float = 1e-8
+    rmax: int = 2 ** 62
+    S_alg: Optional[SubStepper] = None
+    L_alg: Optional[SubStepper] = None
+    K_alg: Optional[SubStepper] = None
+
+
+@dataclass
+class GreedyIntegrator:
+    pass
+
+
+# ------------------------------------------------------------------------------------------------
+# init / step! / solve
+# ------------------------------------------------------------------------------------------------
+
+
+def _fetch(y, t, dt):
+    """update_data! (data_integrator.jl:22-28)."""
+    if callable(y):
+        return y(t + dt)
+    if not (isinstance(t, (int, np.integer)) and isinstance(dt, (int, np.integer))):
+        raise TypeError("MethodError: update_data!(x, y::AbstractArray, t::Int, dt::Int) needs integer t and dt")
+    return y[t + dt - 1]
+
+
+def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False) -> DLRIntegrator:
+    """init(prob, alg, dt): projector_splitting.jl:107-115, unconventional.jl:109-119,
+    rank_adaptive_unconventional.jl:94-104, greedy_integrator.jl:49-59.  `comm` = (nranks, rank, unique_id) row-shards
+    the problem: every rank passes ITS row block of u0.U and of the snapshots."""
+    t0, tf = prob.tspan
+    assert tf > t0, "Integration in reverse time direction is not supported"
+    u0 = prob.u0
+    n, r0 = u0.U.shape
+    m = u0.V.shape[0]
+    adaptive = isinstance(alg, RankAdaptiveUnconventionalAlgorithm)
+    rmax = r0
+    if adaptive:
+        rmax = int(min(alg.rmax, 128, m // 2 if m >= 2 else 1))
+        rmax = max(rmax, r0)
+    eng = Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic)
+    if comm is not None and comm[0] > 1:
+        eng.comm_init(*comm)
+    eng.set_factors(u0.U, u0.S, u0.V)  # deepcopy(prob.u0)
+    if isinstance(prob, MatrixDataProblem):
+        y = prob.y
+        eng.data_init(y(t0) if callable(y) else y[0])  # yprev = y[1] | y(t0)
+    else:
+        if isinstance(alg, GreedyIntegrator):
+            raise TypeError("MethodError: GreedyIntegrator is defined for data problems")
+        prob.f.install(eng)
+        for flow, sub in ((L.FLOW_K, alg.K_alg), (L.FLOW_S, alg.S_alg), (L.FLOW_L, alg.L_alg)):
+            sub = sub or SubStepper()
+            eng.set_substepper(flow, _ODE[sub.kind], sub.nsub, sub.abstol, sub.reltol)
+    sol = init_sol(dt, t0, tf, u0)
+    sol.Y[0] = u0.copy() if hasattr(u0, "copy") else u0
+    return DLRIntegrator(eng, t0, dt, sol, alg, type(prob), prob, save_everystep)
+
+
+def step(integ: DLRIntegrator, alg=None, dt=None):
+    """step!(integrator, alg, dt): projector_splitting.jl:191-211, unconventional.jl:159-164,
+    rank_adaptive_unconventional.jl:171-180, greedy_integrator.jl:106-111."""
+    alg = integ.alg if alg is None else alg
+    dt = integ.dt if dt is None else dt
+    eng, t = integ.cache, integ.t
+    is_data = integ.probType is MatrixDataProblem
+    y = integ.prob.y if is_data else None
+    if isinstance(alg, ProjectorSplitting):
+        if isinstance(alg.order, Strang):
+            if is_data:  # each half fetches its own increment (projector_splitting.jl:205-211)
+                eng.data_push(_fetch(y, t, dt / 2))
+                eng.step_ksl(L.KSL_PRIMAL, t, dt / 2)
+                eng.data_push(_fetch(y, t + dt / 2, dt / 2))
+                eng.step_ksl(L.KSL_DUAL, t + dt / 2, dt / 2)
+            else:
+                eng.step_ksl(L.KSL_STRANG, t, dt)
+        else:
+            if is_data:
+                eng.data_push(_fetch(y, t, dt))
+            eng.step_ksl(L.KSL_PRIMAL if isinstance(alg.order, PrimalLieTrotter) else L.KSL_DUAL, t, dt)
+    elif isinstance(alg, UnconventionalAlgorithm):
+        if is_data:
+            eng.data_push(_fetch(y, t, dt))
+        eng.step_bug(t, dt)
+    elif isinstance(alg, RankAdaptiveUnconventionalAlgorithm):
+        if is_data:
+            eng.data_push(_fetch(y, t, dt))
+        r_new, changed = eng.step_rabug(alg.tol, alg.rmax, t, dt)
+        if changed:
+            print(f"rank adjusted: new rank = {r_new}")  # rank_adaptive_unconventional.jl:230
+    elif isinstance(alg, GreedyIntegrator):
+        eng.data_push(_fetch(y, t, dt))
+        eng.step_greedy(t, dt)
+    else:
+        raise TypeError(f"MethodError: no step! for {type(alg).__name__}")
+    integ.t += dt
+    integ.iter += 1
+
+
+def solve(prob, alg, dt=None, **kw) -> DLRSolution:
+    """LowRankIntegrators.solve (primitives.jl:68-80)."""
+    if dt is None:
+        assert isinstance(prob, MatrixDataProblem) and not callable(prob.y), (
+            "If the data is not provided as array, integration stepsize needs to be specified")
+        dt = 1
+    integ = init(prob, alg, dt, **kw)
+    T = prob.tspan[1] - prob.tspan[0]
+    while (prob.tspan[1] - integ.t) / T > 1e-8:
+        step(integ, alg, dt)
+        update_sol(integ)
+    if not integ.save_everystep:
+        integ.sol.Y[-1] = integ.u
+    integ.cache.sync()
+    return integ.sol

@@ -1,0 +1,646 @@
+// libdlra.so — C ABI (include/dlra.h) and the per-step orchestration of the KSL / BUG / rank-adaptive BUG
+// integrators on one B200.  Step algebra follows SURVEY.md Appendix A, which restates
+// src/integrators/projector_splitting.jl:117-189, unconventional.jl:121-157 and
+// rank_adaptive_unconventional.jl:182-233 of the reference.  No CPU fallback exists: every entry point
+// needs a CUDA device.
+#include "engine.cuh"
+#include "passes.cuh"
+#include "de_flows.cuh"
+
+using namespace dlra;
+
+static thread_local std::string g_create_error;
+
+#define DLRA_API_BEGIN(h)                                                     \
+    if (!(h)) { g_create_error = "null handle"; return DLRA_EINVAL; }         \
+    try {                                                                     \
+        DLRA_CUDA(cudaSetDevice((h)->device));
+
+#define DLRA_API_END(h)                                                       \
+    }                                                                         \
+    catch (const CudaError& ex) { (h)->err = ex.what(); return ex.code; }     \
+    catch (const std::exception& ex) { (h)->err = ex.what(); return DLRA_ECUDA; } \
+    return DLRA_OK;
+
+// ---------------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------------
+extern "C" const char* dlra_version(void) { return "dlra-b200 0.1 (sm_100a)"; }
+
+extern "C" const char* dlra_last_error(dlra_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int rmax, int flags, dlra_handle* out) {
+    if (!out) { g_create_error = "out == NULL"; return DLRA_EINVAL; }
+    *out = nullptr;
+    if (n_local < 1 || m < 1 || r0 < 1 || rmax < r0 || rmax > 128 || rmax > m) {
+        g_create_error = "dlra_create: need n_local >= 1, m >= 1, 1 <= r0 <= rmax <= min(128, m)";
+        return DLRA_EINVAL;
+    }
+    dlra_engine* e = new dlra_engine();
+    try {
+        int ndev = 0;
+        DLRA_CUDA(cudaGetDeviceCount(&ndev));
+        DLRA_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+        DLRA_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        DLRA_CUDA(cudaGetDeviceProperties(&prop, device));
+        DLRA_REQUIRE(prop.major >= 10, "libdlra.so is built for sm_100a (B200) only");
+        e->device = device;
+        e->n = n_local; e->m = m; e->r = r0; e->rmax = rmax; e->flags = flags;
+        e->W = (flags & DLRA_RANK_ADAPTIVE) ? 2 * rmax : rmax;
+        e->cx.num_sms = prop.multiProcessorCount;
+        DLRA_CUDA(cudaStreamCreateWithFlags(&e->cx.stream, cudaStreamNonBlocking));
+        DLRA_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        const int64_t W = e->W;
+        auto dmalloc = [&](int64_t doubles) {
+            double* p = nullptr;
+            cudaError_t er = cudaMalloc(&p, (size_t)doubles * 8);
+            if (er != cudaSuccess) throw CudaError(5, std::string("cudaMalloc failed: ") + cudaGetErrorString(er));
+            DLRA_CUDA(cudaMemsetAsync(p, 0, (size_t)doubles * 8, e->cx.stream));
+            return p;
+        };
+        e->U = dmalloc(e->n * W); e->UB = dmalloc(e->n * W);
+        e->V = dmalloc(e->m * W); e->VB = dmalloc(e->m * W);
+        e->small_block = dmalloc(10 * W * W + 64);
+        double* sb = e->small_block;
+        e->S = sb; sb += W * W; e->M = sb; sb += W * W; e->N = sb; sb += W * W; e->Sh = sb; sb += W * W;
+        e->T1 = sb; sb += W * W; e->T2 = sb; sb += W * W; e->Rm = sb; sb += W * W; e->Pm = sb; sb += W * W;
+        e->Qm = sb; sb += W * W; e->sig = sb; sb += W; e->scal_dev = sb + W;
+        DLRA_CUDA(cudaMalloc(&e->r_new_dev, sizeof(int)));
+        DLRA_CUDA(cudaHostAlloc(&e->r_new_host, sizeof(int), cudaHostAllocDefault));
+        *e->r_new_host = r0;
+        for (int i = 0; i < 3; ++i) {
+            DLRA_CUDA(cudaEventCreateWithFlags(&e->own_free[i], cudaEventDisableTiming));
+            DLRA_CUDA(cudaEventCreateWithFlags(&e->own_ready[i], cudaEventDisableTiming));
+        }
+        e->sub[0] = SubStepperCfg(); e->sub[1] = SubStepperCfg(); e->sub[2] = SubStepperCfg();
+        DLRA_CUDA(cudaStreamSynchronize(e->cx.stream));
+    } catch (const CudaError& ex) {
+        g_create_error = ex.what();
+        int code = ex.code;
+        delete e;
+        return code;
+    }
+    *out = e;
+    return DLRA_OK;
+}
+
+extern "C" int dlra_destroy(dlra_handle h) {
+    if (!h) return DLRA_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->cx.stream);
+    cudaStreamSynchronize(h->copy_stream);
+    h->comm.destroy();
+    cudaFree(h->U); cudaFree(h->UB); cudaFree(h->V); cudaFree(h->VB); cudaFree(h->small_block);
+    cudaFree(h->r_new_dev); cudaFreeHost(h->r_new_host);
+    for (int i = 0; i < 3; ++i) { if (h->own[i]) cudaFree(h->own[i]); cudaEventDestroy(h->own_free[i]); cudaEventDestroy(h->own_ready[i]); }
+    h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release();
+    for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    de_release(h);
+    cudaStreamDestroy(h->cx.stream); cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return DLRA_OK;
+}
+
+extern "C" int dlra_sync(dlra_handle h) {
+    DLRA_API_BEGIN(h)
+    DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));
+    DLRA_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dlra_nccl_unique_id(void* id128) {
+    try {
+        Comm c;
+        c.load();
+        Comm::UniqueId id;
+        c.check(c.pGetUniqueId(&id), "ncclGetUniqueId");
+        memcpy(id128, id.internal, 128);
+    } catch (const CudaError& ex) { g_create_error = ex.what(); return ex.code; }
+    return DLRA_OK;
+}
+
+extern "C" int dlra_comm_init(dlra_handle h, int nranks, int rank, const void* id128) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && id128, "bad communicator arguments");
+    DLRA_REQUIRE(nranks <= 8, "row sharding supports up to 8 ranks (one NVSwitch box)");
+    if (nranks > 1) h->comm.init(nranks, rank, id128);
+    DLRA_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// factors
+// ---------------------------------------------------------------------------------------------------
+static void set_factors_impl(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds, const double* V, int64_t ldv,
+                             int r, cudaMemcpyKind kind) {
+    DLRA_REQUIRE(r >= 1 && r <= h->rmax, "rank outside [1, rmax]");
+    DLRA_REQUIRE(U && S && V && ldu >= h->n && lds >= r && ldv >= h->m, "bad factor pointers / leading dimensions");
+    cudaStream_t s = h->cx.stream;
+    DLRA_CUDA(cudaMemcpy2DAsync(h->U, h->n * 8, U, ldu * 8, h->n * 8, r, kind, s));
+    DLRA_CUDA(cudaMemcpy2DAsync(h->V, h->m * 8, V, ldv * 8, h->m * 8, r, kind, s));
+    DLRA_CUDA(cudaMemcpy2DAsync(h->S, (size_t)h->W * 8, S, lds * 8, (size_t)r * 8, r, kind, s));
+    h->r = r;
+    if (kind == cudaMemcpyHostToDevice) DLRA_CUDA(cudaStreamSynchronize(s));
+}
+extern "C" int dlra_set_factors_host(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds, const double* V,
+                                     int64_t ldv, int r) {
+    DLRA_API_BEGIN(h)
+    set_factors_impl(h, U, ldu, S, lds, V, ldv, r, cudaMemcpyHostToDevice);
+    DLRA_API_END(h)
+}
+extern "C" int dlra_set_factors(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds, const double* V, int64_t ldv,
+                                int r) {
+    DLRA_API_BEGIN(h)
+    set_factors_impl(h, U, ldu, S, lds, V, ldv, r, cudaMemcpyDeviceToDevice);
+    DLRA_API_END(h)
+}
+static void get_factors_impl(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V, int64_t ldv, int* r,
+                             cudaMemcpyKind kind) {
+    const int rr = h->r;
+    DLRA_REQUIRE(U && S && V && ldu >= h->n && lds >= rr && ldv >= h->m, "bad factor pointers / leading dimensions");
+    cudaStream_t s = h->cx.stream;
+    DLRA_CUDA(cudaMemcpy2DAsync(U, ldu * 8, h->U, h->n * 8, h->n * 8, rr, kind, s));
+    DLRA_CUDA(cudaMemcpy2DAsync(V, ldv * 8, h->V, h->m * 8, h->m * 8, rr, kind, s));
+    DLRA_CUDA(cudaMemcpy2DAsync(S, lds * 8, h->S, (size_t)h->W * 8, (size_t)rr * 8, rr, kind, s));
+    DLRA_CUDA(cudaStreamSynchronize(s));
+    if (r) *r = rr;
+}
+extern "C" int dlra_get_factors_host(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V, int64_t ldv, int* r) {
+    DLRA_API_BEGIN(h)
+    get_factors_impl(h, U, ldu, S, lds, V, ldv, r, cudaMemcpyDeviceToHost);
+    DLRA_API_END(h)
+}
+extern "C" int dlra_get_factors(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V, int64_t ldv, int* r) {
+    DLRA_API_BEGIN(h)
+    get_factors_impl(h, U, ldu, S, lds, V, ldv, r, cudaMemcpyDeviceToDevice);
+    DLRA_API_END(h)
+}
+extern "C" int dlra_get_rank(dlra_handle h, int* r) {
+    if (!h || !r) return DLRA_EINVAL;
+    *r = h->r;
+    return DLRA_OK;
+}
+extern "C" int dlra_factor_ptrs(dlra_handle h, const double** U, int64_t* ldu, const double** S, int64_t* lds, const double** V,
+                                int64_t* ldv, int* r) {
+    if (!h) return DLRA_EINVAL;
+    if (U) *U = h->U; if (ldu) *ldu = h->n;
+    if (S) *S = h->S; if (lds) *lds = h->W;
+    if (V) *V = h->V; if (ldv) *ldv = h->m;
+    if (r) *r = h->r;
+    return DLRA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// data feed
+// ---------------------------------------------------------------------------------------------------
+static int own_slot_for_copy(dlra_handle h) {
+    // rotate over three engine-owned n x m buffers so that an H2D copy for step k+1 overlaps step k
+    int slot = -1;
+    for (int tries = 0; tries < 3; ++tries) {
+        int cand = (h->own_next + tries) % 3;
+        if (cand != h->cur_own && cand != h->prev_own) { slot = cand; break; }
+    }
+    DLRA_REQUIRE(slot >= 0, "no free snapshot buffer");
+    h->own_next = (slot + 1) % 3;
+    if (!h->own[slot]) {
+        cudaError_t er = cudaMalloc(&h->own[slot], (size_t)h->n * h->m * 8);
+        if (er != cudaSuccess) throw CudaError(5, std::string("cudaMalloc(snapshot buffer) failed: ") + cudaGetErrorString(er));
+        DLRA_CUDA(cudaEventRecord(h->own_free[slot], h->cx.stream));
+    }
+    return slot;
+}
+static void copy_host_snapshot(dlra_handle h, int slot, const double* A, int64_t ld) {
+    DLRA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->own_free[slot], 0));
+    DLRA_CUDA(cudaMemcpy2DAsync(h->own[slot], h->n * 8, A, ld * 8, h->n * 8, h->m, cudaMemcpyHostToDevice, h->copy_stream));
+    DLRA_CUDA(cudaEventRecord(h->own_ready[slot], h->copy_stream));
+}
+
+extern "C" int dlra_data_init(dlra_handle h, const double* A0, int64_t ld) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(A0 && ld >= h->n, "bad snapshot pointer / leading dimension");
+    h->prev = A0; h->ldprev = ld; h->prev_own = -1; h->have_cur = false; h->cur_own = -1;
+    DLRA_API_END(h)
+}
+extern "C" int dlra_data_init_host(dlra_handle h, const double* A0, int64_t ld) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(A0 && ld >= h->n, "bad snapshot pointer / leading dimension");
+    h->prev_own = -1; h->cur_own = -1; h->have_cur = false;
+    int slot = own_slot_for_copy(h);
+    copy_host_snapshot(h, slot, A0, ld);
+    DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->own_ready[slot], 0));
+    h->prev = h->own[slot]; h->ldprev = h->n; h->prev_own = slot;
+    DLRA_API_END(h)
+}
+extern "C" int dlra_data_push(dlra_handle h, const double* A, int64_t ld, int kind) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(A && ld >= h->n, "bad snapshot pointer / leading dimension");
+    DLRA_REQUIRE(kind == DLRA_DATA_SNAPSHOT || kind == DLRA_DATA_DELTA, "bad data kind");
+    h->cur = A; h->ldcur = ld; h->cur_kind = kind; h->have_cur = true; h->cur_own = -1;
+    DLRA_API_END(h)
+}
+extern "C" int dlra_data_push_host(dlra_handle h, const double* A, int64_t ld, int kind) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(A && ld >= h->n, "bad snapshot pointer / leading dimension");
+    DLRA_REQUIRE(kind == DLRA_DATA_SNAPSHOT || kind == DLRA_DATA_DELTA, "bad data kind");
+    int slot = own_slot_for_copy(h);
+    copy_host_snapshot(h, slot, A, ld);
+    h->cur = h->own[slot]; h->ldcur = h->n; h->cur_kind = kind; h->have_cur = true; h->cur_own = slot;
+    DLRA_API_END(h)
+}
+
+// Fetch the increment for this step (A.0 of SURVEY.md Appendix A) and hand back what to do afterwards.
+static Delta begin_data_step(dlra_handle h, bool want_full_snapshot) {
+    DLRA_REQUIRE(h->have_cur, "no data pushed for this step (call dlra_data_push[_host] first)");
+    Delta d;
+    d.A = h->cur; d.lda = h->ldcur;
+    if (h->cur_own >= 0) DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->own_ready[h->cur_own], 0));
+    if (want_full_snapshot) {
+        DLRA_REQUIRE(h->cur_kind == DLRA_DATA_SNAPSHOT, "the greedy step needs the full snapshot (DLRA_DATA_SNAPSHOT)");
+    } else if (h->cur_kind == DLRA_DATA_SNAPSHOT) {
+        DLRA_REQUIRE(h->prev != nullptr, "dlra_data_init[_host] must provide the initial snapshot before SNAPSHOT pushes");
+        d.Aprev = h->prev; d.ldap = h->ldprev;
+    }
+    return d;
+}
+static void end_data_step(dlra_handle h) {
+    // yprev .= ycurr  (projector_splitting.jl:121): a pointer rotation here
+    if (h->cur_kind == DLRA_DATA_SNAPSHOT) {
+        if (h->prev_own >= 0) DLRA_CUDA(cudaEventRecord(h->own_free[h->prev_own], h->cx.stream));
+        h->prev = h->cur; h->ldprev = h->ldcur; h->prev_own = h->cur_own;
+    } else if (h->cur_own >= 0) {
+        DLRA_CUDA(cudaEventRecord(h->own_free[h->cur_own], h->cx.stream));
+    }
+    h->have_cur = false; h->cur_own = -1; h->cur = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// shared step pieces
+// ---------------------------------------------------------------------------------------------------
+static void ensure_qr_ws(dlra_handle h, int64_t rows, int C) {
+    const int cb = std::min(C, 32);
+    h->tws.ensure(tsqr_ws_size(rows, cb, 8), h->cx.stream);
+    if (C > 32) {
+        h->wtmp.ensure((int64_t)C * 32, h->cx.stream);
+        h->gws.ensure(gemm_tn_ws(h->cx, rows, C, 32), h->cx.stream);
+    }
+}
+// thin QR of an n-side (row sharded) matrix, in place
+static void qr_nside(dlra_handle h, double* A, int C, double* R) {
+    ensure_qr_ws(h, h->n, C);
+    thin_qr(h->cx, h->comm, h->n, C, A, h->n, A, h->n, R, h->W, h->tws.p, h->gws.p, h->wtmp.p);
+}
+// thin QR of an m-side (replicated) matrix, in place, computed redundantly on every rank
+static void qr_mside(dlra_handle h, double* A, int C, double* R) {
+    ensure_qr_ws(h, h->m, C);
+    thin_qr(h->cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, h->tws.p, h->gws.p, h->wtmp.p);
+}
+// C (p x q, ld W) = A' * B over the sharded n dimension (+ all-reduce)
+static void gram_nside(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
+    h->gws.ensure(gemm_tn_ws(h->cx, h->n, p, q), h->cx.stream);
+    if (h->comm.nranks > 1) {
+        // reduce into a dense p x q staging block so one collective suffices
+        gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, h->T2, p, 1.0, 0.0, h->gws.p);
+        h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx.stream);
+        copy_mat(h->cx, p, q, h->T2, p, false, C, h->W);
+    } else {
+        gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, C, h->W, 1.0, 0.0, h->gws.p);
+    }
+}
+static void gram_mside(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
+    h->gws.ensure(gemm_tn_ws(h->cx, h->m, p, q), h->cx.stream);
+    gemm_tn(h->cx, h->m, p, q, A, h->m, nullptr, 0, B, h->m, C, h->W, 1.0, 0.0, h->gws.p);
+}
+// dense m x r all-reduce of an m-side matrix with ld == m
+static void allreduce_mside(dlra_handle h, double* L, int r) { h->comm.allreduce_sum(L, h->m * (int64_t)r, h->cx.stream); }
+// p x q small matrix with ld W: stage densely, reduce, copy back
+static void allreduce_small(dlra_handle h, double* C, int p, int q) {
+    if (h->comm.nranks <= 1) return;
+    copy_mat(h->cx, p, q, C, h->W, false, h->T2, p);
+    h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx.stream);
+    copy_mat(h->cx, p, q, h->T2, p, false, C, h->W);
+}
+
+// K-flow / L-flow / S-flow of one outer step: data problems contract the increment, DE problems integrate
+// the projected right-hand side (de_flows.cuh).  `Kbuf` holds K0 on entry and K1 on exit, etc.
+struct StepCtx {
+    bool is_data;
+    Delta d;
+    double t, dt;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// unconventional (BUG) step — unconventional.jl:133-157, SURVEY.md A.2
+// ---------------------------------------------------------------------------------------------------
+static void bug_step(dlra_handle h, const StepCtx& sc) {
+    Ctx& cx = h->cx;
+    const int r = h->r;
+    const int64_t n = h->n, m = h->m, W = h->W;
+    double *K = h->UB, *L = h->VB;
+    // K = U0*S0 (+ ΔA*V0);  L = V0*S0' (+ ΔA'*U0)   — one fused read of ΔA
+    gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);
+    if (sc.is_data) {
+        pass_KL(h, sc.d, r, h->V, m, h->U, n, K, n, L, m);
+        allreduce_mside(h, L, r);
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 1.0);
+    } else {
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 0.0);
+        de_K_flow(h, K, r, h->V, sc.t, sc.dt);
+        de_L_flow(h, L, r, h->U, sc.t, sc.dt);
+    }
+    qr_nside(h, K, r, nullptr);                 // U1 = qr(K).Q
+    gram_nside(h, r, r, K, h->U, h->M);         // M = U1'*U0
+    qr_mside(h, L, r, nullptr);                 // V1 = qr(L).Q
+    gram_mside(h, r, r, L, h->V, h->N);         // N = V1'*V0
+    small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);   // T1 = M*S0
+    small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);   // Sh = M*S0*N'
+    if (sc.is_data) {
+        pass_S(h, sc.d, r, r, K, n, L, m, h->T1, W);            // T1 = U1'*ΔA*V1 (local rows)
+        allreduce_small(h, h->T1, r, r);
+        copy_mat(cx, r, r, h->T1, W, false, h->Sh, W, 1.0, 1.0);
+    } else {
+        de_S_flow(h, h->Sh, r, r, K, L, +1.0, sc.t, sc.dt);
+    }
+    std::swap(h->U, h->UB);
+    std::swap(h->V, h->VB);
+    copy_mat(cx, r, r, h->Sh, W, false, h->S, W);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// projector splitting (KSL) — projector_splitting.jl:129-152 (primal), 166-189 (dual), SURVEY.md A.1
+// ---------------------------------------------------------------------------------------------------
+static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
+    Ctx& cx = h->cx;
+    const int r = h->r;
+    const int64_t n = h->n, m = h->m, W = h->W;
+    double *K = h->UB, *L = h->VB;
+    gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);               // K = U0*S0
+    if (sc.is_data) pass_KL(h, sc.d, r, h->V, m, nullptr, 0, K, n, nullptr, 0);               //   += ΔA*V0
+    else de_K_flow(h, K, r, h->V, sc.t, sc.dt);
+    qr_nside(h, K, r, h->Rm);                                                                 // U1, R
+    if (sc.is_data) {
+        // W = ΔA'*U1 ; S~ = R − W'*V0 ; L = V0*S~' + W        (U1'ΔA V0 == W'V0)
+        pass_KL(h, sc.d, r, nullptr, 0, K, n, nullptr, 0, L, m);
+        allreduce_mside(h, L, r);
+        gram_mside(h, r, r, L, h->V, h->T1);                                                  // T1 = W'*V0
+        copy_mat(cx, r, r, h->Rm, W, false, h->Sh, W);
+        copy_mat(cx, r, r, h->T1, W, false, h->Sh, W, -1.0, 1.0);                             // Sh = R − W'V0
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->Sh, W, true, L, m, 1.0, 1.0);            // L = W + V0*Sh'
+    } else {
+        copy_mat(cx, r, r, h->Rm, W, false, h->Sh, W);
+        de_S_flow(h, h->Sh, r, r, K, h->V, -1.0, sc.t, sc.dt);                                // S-step with (U1, V0), minus sign
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->Sh, W, true, L, m, 1.0, 0.0);            // L0 = V0*S~'
+        de_L_flow(h, L, r, K, sc.t, sc.dt);
+    }
+    qr_mside(h, L, r, h->Rm);                                                                 // V1, R_L
+    copy_mat(cx, r, r, h->Rm, W, true, h->S, W);                                              // S1 = R_L'
+    std::swap(h->U, h->UB);
+    std::swap(h->V, h->VB);
+}
+
+static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
+    Ctx& cx = h->cx;
+    const int r = h->r;
+    const int64_t n = h->n, m = h->m, W = h->W;
+    double *K = h->UB, *L = h->VB;
+    if (sc.is_data) {
+        pass_KL(h, sc.d, r, nullptr, 0, h->U, n, nullptr, 0, L, m);                           // L = ΔA'*U0
+        allreduce_mside(h, L, r);
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 1.0);             //   + V0*S0'
+    } else {
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 0.0);
+        de_L_flow(h, L, r, h->U, sc.t, sc.dt);
+    }
+    qr_mside(h, L, r, h->Rm);                                                                 // V1, R_L
+    copy_mat(cx, r, r, h->Rm, W, true, h->Sh, W);                                             // Sh = R_L'
+    if (sc.is_data) {
+        // Wn = ΔA*V1 ; S~ = R_L' − U0'*Wn ; K = U0*S~ + Wn
+        fill_mat(cx, n, r, K, n, 0.0, 0.0);
+        pass_KL(h, sc.d, r, L, m, nullptr, 0, K, n, nullptr, 0);
+        gram_nside(h, r, r, h->U, K, h->T1);                                                  // T1 = U0'*Wn
+        copy_mat(cx, r, r, h->T1, W, false, h->Sh, W, -1.0, 1.0);
+        gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->Sh, W, false, K, n, 1.0, 1.0);
+    } else {
+        de_S_flow(h, h->Sh, r, r, h->U, L, -1.0, sc.t, sc.dt);                                // S-step with (U0, V1)
+        gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->Sh, W, false, K, n, 1.0, 0.0);           // K0 = U0*S~
+        de_K_flow(h, K, r, L, sc.t, sc.dt);
+    }
+    qr_nside(h, K, r, h->Rm);                                                                 // U1, R
+    copy_mat(cx, r, r, h->Rm, W, false, h->S, W);                                             // S1 = R
+    std::swap(h->U, h->UB);
+    std::swap(h->V, h->VB);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// rank-adaptive BUG — rank_adaptive_unconventional.jl:194-233 + alg_recache :133-169, SURVEY.md A.3
+// ---------------------------------------------------------------------------------------------------
+static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rcap64, int* r_new_out, int* changed) {
+    Ctx& cx = h->cx;
+    const int r = h->r;
+    const int r2 = 2 * r;
+    const int64_t n = h->n, m = h->m, W = h->W;
+    DLRA_REQUIRE(h->flags & DLRA_RANK_ADAPTIVE, "handle was created without DLRA_RANK_ADAPTIVE");
+    DLRA_REQUIRE(r2 <= W, "augmented basis exceeds workspace");
+    DLRA_REQUIRE(r2 <= m, "augmented basis wider than the matrix");
+    int rcap = (int)std::min<int64_t>(rcap64, (int64_t)h->rmax);
+    rcap = std::min(rcap, r2);
+    double *Kh = h->UB, *Lh = h->VB;   // [K U0] -> Uhat ; [L V0] -> Vhat
+    gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, Kh, n, 1.0, 0.0);
+    if (sc.is_data) {
+        pass_KL(h, sc.d, r, h->V, m, h->U, n, Kh, n, Lh, m);
+        allreduce_mside(h, Lh, r);
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, Lh, m, 1.0, 1.0);
+    } else {
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, Lh, m, 1.0, 0.0);
+        de_K_flow(h, Kh, r, h->V, sc.t, sc.dt);
+        de_L_flow(h, Lh, r, h->U, sc.t, sc.dt);
+    }
+    copy_mat(cx, n, r, h->U, n, false, Kh + (int64_t)r * n, n);          // Uhat[:, r+1:end] = U0
+    copy_mat(cx, m, r, h->V, m, false, Lh + (int64_t)r * m, m);
+    qr_nside(h, Kh, r2, nullptr);
+    gram_nside(h, r2, r, Kh, h->U, h->M);                                // M = Uhat'*U0 (2r x r)
+    qr_mside(h, Lh, r2, nullptr);
+    gram_mside(h, r2, r, Lh, h->V, h->N);                                // N = Vhat'*V0
+    small_gemm(cx, r2, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);
+    small_gemm(cx, r2, r2, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);
+    if (sc.is_data) {
+        pass_S(h, sc.d, r2, r2, Kh, n, Lh, m, h->T1, W);
+        allreduce_small(h, h->T1, r2, r2);
+        copy_mat(cx, r2, r2, h->T1, W, false, h->Sh, W, 1.0, 1.0);
+    } else {
+        de_S_flow(h, h->Sh, r2, r2, Kh, Lh, +1.0, sc.t, sc.dt);
+    }
+    h->jws.ensure((int64_t)jacobi_ws_doubles(r2), cx.stream);
+    jacobi_svd(cx, r2, h->Sh, (int)W, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, tol, rcap, h->r_new_dev, nullptr);
+    DLRA_CUDA(cudaMemcpyAsync(h->r_new_host, h->r_new_dev, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
+    DLRA_CUDA(cudaStreamSynchronize(cx.stream));
+    const int r1 = *h->r_new_host;
+    DLRA_REQUIRE(r1 >= 1 && r1 <= rcap, "rank selection returned an impossible rank");
+    gemm_nn(cx, n, r2, r1, Kh, n, nullptr, 0, h->Pm, W, false, h->U, n, 1.0, 0.0);   // U1 = Uhat*P[:, 1:r1]
+    gemm_nn(cx, m, r2, r1, Lh, m, nullptr, 0, h->Qm, W, false, h->V, m, 1.0, 0.0);   // V1 = Vhat*Q[:, 1:r1]
+    fill_mat(cx, r1, r1, h->S, W, 0.0, 0.0);
+    copy_mat(cx, 1, r1, h->sig, 1, false, h->S, W + 1);                              // S1 = Diagonal(sigma[1:r1])
+    if (changed) *changed = (r1 != r) ? 1 : 0;
+    if (r_new_out) *r_new_out = r1;
+    h->r = r1;
+    if (r1 != r) de_rank_changed(h);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// greedy re-projection — greedy_integrator.jl:94-104
+// ---------------------------------------------------------------------------------------------------
+static void greedy_step(dlra_handle h, const Delta& x) {
+    Ctx& cx = h->cx;
+    const int r = h->r;
+    const int64_t n = h->n, m = h->m, W = h->W;
+    double *XV = h->UB, *XU = h->VB;
+    fill_mat(cx, n, r, XV, n, 0.0, 0.0);
+    pass_KL(h, x, r, h->V, m, h->U, n, XV, n, XU, m);        // XV = X*V ; XU = X'*U
+    allreduce_mside(h, XU, r);
+    qr_nside(h, XV, r, nullptr);
+    qr_mside(h, XU, r, nullptr);
+    pass_S(h, x, r, r, XV, n, XU, m, h->T1, W);              // S = U1'*X*V1
+    allreduce_small(h, h->T1, r, r);
+    copy_mat(cx, r, r, h->T1, W, false, h->S, W);
+    std::swap(h->U, h->UB);
+    std::swap(h->V, h->VB);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// step entry points
+// ---------------------------------------------------------------------------------------------------
+static StepCtx make_ctx(dlra_handle h, double t, double dt) {
+    StepCtx sc;
+    sc.t = t; sc.dt = dt;
+    sc.is_data = !h->rhs.set;
+    if (sc.is_data) sc.d = begin_data_step(h, false);
+    return sc;
+}
+
+extern "C" int dlra_step_ksl(dlra_handle h, int order, double t, double dt) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(order == DLRA_KSL_PRIMAL || order == DLRA_KSL_DUAL || order == DLRA_KSL_STRANG, "bad KSL order");
+    if (order == DLRA_KSL_STRANG) {
+        DLRA_REQUIRE(h->rhs.set, "Strang on a data problem needs two increments: push, PRIMAL(dt/2), push, DUAL(dt/2)");
+        StepCtx a; a.is_data = false; a.t = t; a.dt = dt / 2;
+        ksl_primal_step(h, a);
+        StepCtx b; b.is_data = false; b.t = t + dt / 2; b.dt = dt / 2;
+        ksl_dual_step(h, b);
+    } else {
+        StepCtx sc = make_ctx(h, t, dt);
+        if (order == DLRA_KSL_PRIMAL) ksl_primal_step(h, sc); else ksl_dual_step(h, sc);
+        if (sc.is_data) end_data_step(h);
+    }
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_step_bug(dlra_handle h, double t, double dt) {
+    DLRA_API_BEGIN(h)
+    StepCtx sc = make_ctx(h, t, dt);
+    bug_step(h, sc);
+    if (sc.is_data) end_data_step(h);
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_step_rabug(dlra_handle h, double t, double dt, double tol, int64_t rmax, int* r_new, int* rank_changed) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(tol >= 0.0 && rmax >= 1, "bad tolerance / rank cap");
+    StepCtx sc = make_ctx(h, t, dt);
+    rabug_step(h, sc, tol, rmax, r_new, rank_changed);
+    if (sc.is_data) end_data_step(h);
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_step_greedy(dlra_handle h, double t, double dt) {
+    (void)t; (void)dt;
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(!h->rhs.set, "the greedy integrator is defined for data problems");
+    Delta x = begin_data_step(h, true);
+    greedy_step(h, x);
+    end_data_step(h);
+    DLRA_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DE problem configuration
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dlra_rhs_set(dlra_handle h, const dlra_operator* A, const dlra_operator* B, const double* G, int64_t ldg,
+                            const double* H, int64_t ldh, int q, const dlra_operator* D1, const dlra_operator* D2, double c_had) {
+    DLRA_API_BEGIN(h)
+    de_rhs_set(h, A, B, G, ldg, H, ldh, q, D1, D2, c_had);
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_set_substepper(dlra_handle h, int flow, int ode, int nsub, double abstol, double reltol) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(flow >= 0 && flow <= 2, "flow must be DLRA_FLOW_K|S|L");
+    DLRA_REQUIRE(ode >= DLRA_ODE_EULER && ode <= DLRA_ODE_TSIT5, "unknown sub-stepper");
+    DLRA_REQUIRE(nsub >= 1, "nsub >= 1");
+    SubStepperCfg c;
+    c.ode = ode; c.nsub = nsub;
+    if (abstol > 0) c.abstol = abstol;
+    if (reltol > 0) c.reltol = reltol;
+    h->sub[flow] = c;
+    DLRA_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// diagnostics
+// ---------------------------------------------------------------------------------------------------
+extern "C" int dlra_reconstruct(dlra_handle h, double* Y, int64_t ld) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(Y && ld >= h->n, "bad output");
+    const int r = h->r;
+    h->nscr.ensure(h->n * (int64_t)r, h->cx.stream);
+    gemm_nn(h->cx, h->n, r, r, h->U, h->n, nullptr, 0, h->S, h->W, false, h->nscr.p, h->n, 1.0, 0.0);   // US
+    gemm_nn(h->cx, h->n, r, (int)h->m, h->nscr.p, h->n, nullptr, 0, h->V, h->m, true, Y, ld, 1.0, 0.0); // US*V'
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_reconstruct_error(dlra_handle h, const double* Yref, int64_t ld, double* rel_fro) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(Yref && ld >= h->n && rel_fro, "bad arguments");
+    const int r = h->r;
+    h->nscr.ensure(h->n * (int64_t)r, h->cx.stream);
+    gemm_nn(h->cx, h->n, r, r, h->U, h->n, nullptr, 0, h->S, h->W, false, h->nscr.p, h->n, 1.0, 0.0);
+    dim3 grid((unsigned)cdiv(h->n, 128), (unsigned)cdiv(h->m, 512));
+    const int64_t nblocks = (int64_t)grid.x * grid.y;
+    h->gws.ensure(2 * nblocks + 16, h->cx.stream);
+    recon_err_kernel<<<grid, 128, (size_t)r * 8 * sizeof(double), h->cx.stream>>>(h->n, h->m, r, h->nscr.p, h->n, h->V, h->m, Yref, ld, h->gws.p);
+    h->cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+    sum_pairs_kernel<<<1, 1024, 0, h->cx.stream>>>(nblocks, h->gws.p, h->scal_dev);
+    h->cx.launches++;
+    h->comm.allreduce_sum(h->scal_dev, 2, h->cx.stream);
+    double out[2];
+    DLRA_CUDA(cudaMemcpyAsync(out, h->scal_dev, 16, cudaMemcpyDeviceToHost, h->cx.stream));
+    DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));
+    *rel_fro = (out[1] > 0.0) ? sqrt(out[0] / out[1]) : sqrt(out[0]);
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_set_profiling(dlra_handle h, int time_passes) {
+    if (!h) return DLRA_EINVAL;
+    h->time_passes = time_passes != 0;
+    return DLRA_OK;
+}
+
+extern "C" int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass_launches, double* pass_ms_total,
+                          double* pass_bytes_total, int reset) {
+    DLRA_API_BEGIN(h)
+    DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));
+    for (auto& pr : h->pass_events) {
+        float ms = 0.f;
+        DLRA_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+        h->pass_ms += ms;
+        cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
+    }
+    h->pass_events.clear();
+    if (kernel_launches) *kernel_launches = h->cx.launches;
+    if (pass_launches) *pass_launches = h->pass_launches;
+    if (pass_ms_total) *pass_ms_total = h->pass_ms;
+    if (pass_bytes_total) *pass_bytes_total = h->pass_bytes;
+    if (reset) { h->cx.launches = 0; h->pass_launches = 0; h->pass_ms = 0.0; h->pass_bytes = 0.0; }
+    DLRA_API_END(h)
+}

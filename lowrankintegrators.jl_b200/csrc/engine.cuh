@@ -1,0 +1,95 @@
+// Engine state behind a dlra_handle: device-resident factors, workspaces sized once for rmax
+// (no alg_recache-style reallocation, cf. rank_adaptive_unconventional.jl:133-169), the data feed and streams.
+#pragma once
+#include "common.cuh"
+#include "comm.cuh"
+#include "small_ops.cuh"
+#include "tsqr.cuh"
+#include "jacobi.cuh"
+#include "../../include/dlra.h"
+#include <vector>
+#include <algorithm>
+
+namespace dlra {
+
+struct DevBuf {
+    double* p = nullptr;
+    int64_t n = 0;  // doubles
+    void ensure(int64_t want, cudaStream_t s) {
+        if (want <= n) return;
+        if (p) { DLRA_CUDA(cudaStreamSynchronize(s)); DLRA_CUDA(cudaFree(p)); p = nullptr; n = 0; }
+        cudaError_t e = cudaMalloc(&p, (size_t)want * sizeof(double));
+        if (e != cudaSuccess) { p = nullptr; throw CudaError(5, std::string("cudaMalloc of ") + std::to_string(want * 8) + " bytes failed: " + cudaGetErrorString(e)); }
+        n = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+// ΔA = A − Aprev (Aprev == nullptr: A is the increment itself, or the full snapshot for the greedy step)
+struct Delta {
+    const double* A = nullptr;
+    int64_t lda = 0;
+    const double* Aprev = nullptr;
+    int64_t ldap = 0;
+};
+
+struct SubStepperCfg {
+    int ode = DLRA_ODE_TSIT5;
+    int nsub = 1;
+    double abstol = 1e-6, reltol = 1e-3;
+    // adaptive controller state carried across outer steps (mirrors oracle.SubStepper)
+    double dt_next = -1.0;
+    double qold = 1e-4;
+    int64_t nfev = 0, naccept = 0, nreject = 0;
+};
+
+struct RhsCfg {
+    bool set = false;
+    dlra_operator A{}, B{}, D1{}, D2{};
+    const double* G = nullptr; int64_t ldg = 0;
+    const double* H = nullptr; int64_t ldh = 0;
+    int q = 0;
+    double c_had = 0.0;
+};
+
+}  // namespace dlra
+
+struct dlra_engine {
+    int device = 0;
+    int64_t n = 0, m = 0;       // local rows, columns
+    int r = 0, rmax = 0, flags = 0;
+    int W = 0;                  // widest factor block (rmax, or 2*rmax when rank adaptive)
+    dlra::Ctx cx;
+    dlra::Comm comm;            // row-shard communicator
+    dlra::Comm self;            // nranks = 1: for replicated (m-side) factorizations
+    cudaStream_t copy_stream = nullptr;
+    std::string err;
+
+    // factors (ld: U -> n, V -> m, small -> W)
+    double *U = nullptr, *UB = nullptr, *V = nullptr, *VB = nullptr, *S = nullptr;
+    // small matrices, each W x W, ld = W
+    double *M = nullptr, *N = nullptr, *Sh = nullptr, *T1 = nullptr, *T2 = nullptr, *Rm = nullptr, *Pm = nullptr, *Qm = nullptr, *sig = nullptr;
+    double* small_block = nullptr;
+    int* r_new_dev = nullptr;
+    int* r_new_host = nullptr;  // pinned, mapped
+    double* scal_dev = nullptr; // 8 doubles of device scalars
+    dlra::DevBuf gws, tws, wtmp, jws, nscr, mscr, part;  // grow-on-demand scratch
+
+    // data feed
+    const double* prev = nullptr; int64_t ldprev = 0;
+    const double* cur = nullptr; int64_t ldcur = 0; int cur_kind = 0; bool have_cur = false;
+    double* own[3] = {nullptr, nullptr, nullptr};
+    cudaEvent_t own_free[3] = {nullptr, nullptr, nullptr};   // recorded on the compute stream when a step stops reading own[i]
+    cudaEvent_t own_ready[3] = {nullptr, nullptr, nullptr};  // recorded on the copy stream when the H2D copy landed
+    int own_next = 0; int cur_own = -1; int prev_own = -1;
+
+    // DE problems
+    dlra::RhsCfg rhs;
+    dlra::SubStepperCfg sub[3];
+
+    // profiling of the dominant contraction kernels
+    bool time_passes = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pass_events;
+    int64_t pass_launches = 0;
+    double pass_bytes = 0.0, pass_ms = 0.0;
+};

@@ -1,0 +1,291 @@
+// Generic fp64 helpers: tall-skinny GEMMs (any shape / alignment), tiny dense ops, norms.
+// These carry (a) every O((n+m) r^2) product of a step: U*S, V*S', M = U1'U0, N = V1'V0, M*S*N', Uhat*P
+// (reference: mul! at projector_splitting.jl:133,145,170,182; unconventional.jl:137,142,145,150,154;
+// rank_adaptive_unconventional.jl:198,206,209,217,219,225,227,231) and (b) the generic fallback of the
+// K/L/S contractions `u .+= sign*left'*Δy*right` (data_integrator.jl:13-16) for shapes the TMA/DMMA
+// fast path (pass_tma.cuh) does not take.  All matrices column-major.
+#pragma once
+#include "common.cuh"
+
+namespace dlra {
+
+// ------------------------------------------------------------------------------------------------
+// C[n x q] = beta*C + alpha * (A - Aprev)[n x p] * op(B)[p x q]        (tall A, small op(B); one thread per row)
+// transB: op(B)[k][c] = B[c + k*ldb]  (B stored q x p)
+// ------------------------------------------------------------------------------------------------
+template <int QC>
+__global__ void __launch_bounds__(128) gemm_nn_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
+                                                       const double* __restrict__ Aprev, int64_t ldap,
+                                                       const double* __restrict__ B, int64_t ldb, int transB,
+                                                       double* __restrict__ C, int64_t ldc, double alpha, double beta) {
+    constexpr int KT = 64;
+    __shared__ double Bs[KT][QC];
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int c0 = blockIdx.y * QC;
+    double acc[QC];
+#pragma unroll
+    for (int c = 0; c < QC; ++c) acc[c] = 0.0;
+    for (int k0 = 0; k0 < p; k0 += KT) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < KT * QC; e += 128) {
+            int k = e / QC, c = e % QC;
+            double v = 0.0;
+            if (k0 + k < p && c0 + c < q) v = transB ? B[(c0 + c) + (int64_t)(k0 + k) * ldb] : B[(k0 + k) + (int64_t)(c0 + c) * ldb];
+            Bs[k][c] = v;
+        }
+        __syncthreads();
+        if (i < n) {
+            const int kmax = min(KT, p - k0);
+            for (int k = 0; k < kmax; ++k) {
+                double a = A[i + (int64_t)(k0 + k) * lda];
+                if (Aprev) a -= Aprev[i + (int64_t)(k0 + k) * ldap];
+#pragma unroll
+                for (int c = 0; c < QC; ++c) acc[c] = fma(a, Bs[k][c], acc[c]);
+            }
+        }
+    }
+    if (i < n) {
+#pragma unroll
+        for (int c = 0; c < QC; ++c)
+            if (c0 + c < q) {
+                double* dst = C + i + (int64_t)(c0 + c) * ldc;
+                *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * acc[c];
+            }
+    }
+}
+
+inline void gemm_nn(Ctx& cx, int64_t n, int p, int q, const double* A, int64_t lda, const double* Aprev, int64_t ldap,
+                    const double* B, int64_t ldb, bool transB, double* C, int64_t ldc, double alpha, double beta) {
+    if (n <= 0 || q <= 0) return;
+    dim3 grid((unsigned)cdiv(n, 128), (unsigned)cdiv(q, 16));
+    gemm_nn_kernel<16><<<grid, 128, 0, cx.stream>>>(n, p, q, A, lda, Aprev, ldap, B, ldb, transB ? 1 : 0, C, ldc, alpha, beta);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cpart[chunk][p x q] = (A - Aprev)[rows of chunk, p]' * B[rows of chunk, q]     (long reduction over rows)
+// followed by a fixed-order reduction over chunks (deterministic; no atomics).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_tn_part_kernel(int64_t n, int p, int q, int64_t chunk_rows,
+                                                           const double* __restrict__ A, int64_t lda,
+                                                           const double* __restrict__ Aprev, int64_t ldap,
+                                                           const double* __restrict__ B, int64_t ldb,
+                                                           double* __restrict__ Cpart) {
+    constexpr int RT = 64, PB = 32, QB = 32;
+    __shared__ double As[PB][RT + 1];
+    __shared__ double Bs[QB][RT + 1];
+    const int a0 = blockIdx.y * PB, b0 = blockIdx.z * QB;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk_rows;
+    const int64_t r1 = min(n, r0 + chunk_rows);
+    const int ta = threadIdx.x % 16, tb = threadIdx.x / 16;
+    double acc00 = 0, acc01 = 0, acc10 = 0, acc11 = 0;
+    const int lr = threadIdx.x % RT, lc = threadIdx.x / RT;  // 4 column groups of 8
+    for (int64_t rr = r0; rr < r1; rr += RT) {
+        __syncthreads();
+        const int64_t i = rr + lr;
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+            int c = lc * 8 + cc;
+            double va = 0.0, vb = 0.0;
+            if (i < r1) {
+                if (a0 + c < p) {
+                    va = A[i + (int64_t)(a0 + c) * lda];
+                    if (Aprev) va -= Aprev[i + (int64_t)(a0 + c) * ldap];
+                }
+                if (b0 + c < q) vb = B[i + (int64_t)(b0 + c) * ldb];
+            }
+            As[c][lr] = va;
+            Bs[c][lr] = vb;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < RT; ++k) {
+            double x0 = As[ta][k], x1 = As[ta + 16][k], y0 = Bs[tb][k], y1 = Bs[tb + 16][k];
+            acc00 = fma(x0, y0, acc00);
+            acc01 = fma(x0, y1, acc01);
+            acc10 = fma(x1, y0, acc10);
+            acc11 = fma(x1, y1, acc11);
+        }
+    }
+    double* out = Cpart + (int64_t)blockIdx.x * p * q;
+    if (a0 + ta < p && b0 + tb < q) out[(a0 + ta) + (int64_t)(b0 + tb) * p] = acc00;
+    if (a0 + ta < p && b0 + tb + 16 < q) out[(a0 + ta) + (int64_t)(b0 + tb + 16) * p] = acc01;
+    if (a0 + ta + 16 < p && b0 + tb < q) out[(a0 + ta + 16) + (int64_t)(b0 + tb) * p] = acc10;
+    if (a0 + ta + 16 < p && b0 + tb + 16 < q) out[(a0 + ta + 16) + (int64_t)(b0 + tb + 16) * p] = acc11;
+}
+
+// C[p x q] (ldc) = beta*C + alpha * sum_chunks part[chunk]   (part: dense p x q per chunk, leading dim ldp)
+__global__ void reduce_parts_kernel(int p, int q, int nchunks, const double* __restrict__ part, int64_t ldp, int64_t chunk_stride,
+                                    double* __restrict__ C, int64_t ldc, double alpha, double beta) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)p * q) return;
+    int a = (int)(e % p), b = (int)(e / p);
+    double s = 0.0;
+    for (int c = 0; c < nchunks; ++c) s += part[(int64_t)c * chunk_stride + a + (int64_t)b * ldp];
+    double* dst = C + a + (int64_t)b * ldc;
+    *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
+}
+
+inline void reduce_parts(Ctx& cx, int p, int q, int nchunks, const double* part, int64_t ldp, int64_t chunk_stride, double* C,
+                         int64_t ldc, double alpha, double beta) {
+    int64_t tot = (int64_t)p * q;
+    if (tot <= 0) return;
+    reduce_parts_kernel<<<(unsigned)cdiv(tot, 256), 256, 0, cx.stream>>>(p, q, nchunks, part, ldp, chunk_stride, C, ldc, alpha, beta);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
+// workspace (doubles) needed by gemm_tn for the partial sums
+inline int64_t gemm_tn_chunks(const Ctx& cx, int64_t n, int p, int q) {
+    int64_t blocks = cdiv(p, 32) * cdiv(q, 32);
+    int64_t want = cdiv((int64_t)4 * cx.num_sms, blocks);
+    int64_t chunk_rows = round_up(cdiv(n, want), 64);
+    if (chunk_rows < 256) chunk_rows = 256;
+    return cdiv(n, chunk_rows);
+}
+inline int64_t gemm_tn_ws(const Ctx& cx, int64_t n, int p, int q) { return gemm_tn_chunks(cx, n, p, q) * p * q; }
+
+// C[p x q] = beta*C + alpha * (A - Aprev)' * B
+inline void gemm_tn(Ctx& cx, int64_t n, int p, int q, const double* A, int64_t lda, const double* Aprev, int64_t ldap,
+                    const double* B, int64_t ldb, double* C, int64_t ldc, double alpha, double beta, double* ws) {
+    if (p <= 0 || q <= 0) return;
+    int64_t nch = gemm_tn_chunks(cx, n, p, q);
+    int64_t chunk_rows = round_up(cdiv(n, nch), 64);
+    nch = cdiv(n, chunk_rows);
+    if (nch < 1) nch = 1;
+    dim3 grid((unsigned)nch, (unsigned)cdiv(p, 32), (unsigned)cdiv(q, 32));
+    gemm_tn_part_kernel<<<grid, 256, 0, cx.stream>>>(n, p, q, chunk_rows, A, lda, Aprev, ldap, B, ldb, ws);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+    reduce_parts(cx, p, q, (int)nch, ws, p, (int64_t)p * q, C, ldc, alpha, beta);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tiny dense helpers (single CTA): C = alpha*op(A)*op(B) + beta*C for matrices up to 256 x 256
+// ------------------------------------------------------------------------------------------------
+__global__ void small_gemm_kernel(int p, int q, int k, const double* __restrict__ A, int lda, int tA,
+                                  const double* __restrict__ B, int ldb, int tB, double* __restrict__ C, int ldc,
+                                  double alpha, double beta) {
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < p * q; e += gridDim.x * blockDim.x) {
+        int i = e % p, j = e / p;
+        double s = 0.0;
+        for (int l = 0; l < k; ++l) {
+            double a = tA ? A[l + (int64_t)i * lda] : A[i + (int64_t)l * lda];
+            double b = tB ? B[j + (int64_t)l * ldb] : B[l + (int64_t)j * ldb];
+            s = fma(a, b, s);
+        }
+        double* dst = C + i + (int64_t)j * ldc;
+        *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
+    }
+}
+inline void small_gemm(Ctx& cx, int p, int q, int k, const double* A, int lda, bool tA, const double* B, int ldb, bool tB,
+                       double* C, int ldc, double alpha, double beta) {
+    if (p <= 0 || q <= 0) return;
+    int blocks = (int)cdiv((int64_t)p * q, 256);
+    small_gemm_kernel<<<blocks, 256, 0, cx.stream>>>(p, q, k, A, lda, tA ? 1 : 0, B, ldb, tB ? 1 : 0, C, ldc, alpha, beta);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
+// dst[rows x cols] (ldd) = alpha * op(src) (+ beta*dst)   — copies, transposes, scaled adds of small/tall matrices
+__global__ void copy_mat_kernel(int64_t rows, int cols, const double* __restrict__ src, int64_t lds, int trans,
+                                double* __restrict__ dst, int64_t ldd, double alpha, double beta) {
+    int64_t tot = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e % rows;
+        int64_t j = e / rows;
+        double v = trans ? src[j + i * lds] : src[i + j * lds];
+        double* d = dst + i + j * ldd;
+        *d = alpha * v + (beta == 0.0 ? 0.0 : beta * (*d));
+    }
+}
+inline void copy_mat(Ctx& cx, int64_t rows, int cols, const double* src, int64_t lds, bool trans, double* dst, int64_t ldd,
+                     double alpha = 1.0, double beta = 0.0) {
+    if (rows <= 0 || cols <= 0) return;
+    int64_t tot = rows * cols;
+    int blocks = (int)std::min<int64_t>(cdiv(tot, 256), 65535);
+    copy_mat_kernel<<<blocks, 256, 0, cx.stream>>>(rows, cols, src, lds, trans ? 1 : 0, dst, ldd, alpha, beta);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
+__global__ void fill_kernel(int64_t rows, int cols, double* __restrict__ dst, int64_t ldd, double v, double diag) {
+    int64_t tot = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t i = e % rows, j = e / rows;
+        dst[i + j * ldd] = (i == j) ? diag : v;
+    }
+}
+inline void fill_mat(Ctx& cx, int64_t rows, int cols, double* dst, int64_t ldd, double v, double diag) {
+    if (rows <= 0 || cols <= 0) return;
+    int blocks = (int)std::min<int64_t>(cdiv(rows * cols, 256), 65535);
+    fill_kernel<<<blocks, 256, 0, cx.stream>>>(rows, cols, dst, ldd, v, diag);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// sum_{i,j} (X[i,:]·W[j,:] - Yref[i,j])^2 and sum Yref^2  (X = U*S n x r, W = V m x r) -> out[2] partial per block
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) recon_err_kernel(int64_t n, int64_t m, int r, const double* __restrict__ X, int64_t ldx,
+                                                        const double* __restrict__ W, int64_t ldw,
+                                                        const double* __restrict__ Y, int64_t ldy, double* __restrict__ part) {
+    constexpr int JT = 8;
+    extern __shared__ double Ws[];  // [r][JT]
+    const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    const int64_t j_begin = (int64_t)blockIdx.y * 512, j_end = min(m, j_begin + 512);
+    double e2 = 0.0, y2 = 0.0;
+    for (int64_t j0 = j_begin; j0 < j_end; j0 += JT) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < r * JT; e += 128) {
+            int c = e / JT, jj = e % JT;
+            Ws[e] = (j0 + jj < j_end) ? W[(j0 + jj) + (int64_t)c * ldw] : 0.0;
+        }
+        __syncthreads();
+        if (i < n) {
+            double acc[JT];
+#pragma unroll
+            for (int jj = 0; jj < JT; ++jj) acc[jj] = 0.0;
+            for (int c = 0; c < r; ++c) {
+                double x = X[i + (int64_t)c * ldx];
+#pragma unroll
+                for (int jj = 0; jj < JT; ++jj) acc[jj] = fma(x, Ws[c * JT + jj], acc[jj]);
+            }
+#pragma unroll
+            for (int jj = 0; jj < JT; ++jj)
+                if (j0 + jj < j_end) {
+                    double y = Y[i + (j0 + jj) * ldy];
+                    double d = acc[jj] - y;
+                    e2 = fma(d, d, e2);
+                    y2 = fma(y, y, y2);
+                }
+        }
+    }
+    e2 = warp_sum(e2);
+    y2 = warp_sum(y2);
+    __shared__ double red[2][4];
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = e2; red[1][w] = y2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t b = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+        part[2 * b] = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        part[2 * b + 1] = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+    }
+}
+__global__ void sum_pairs_kernel(int64_t nblocks, const double* __restrict__ part, double* __restrict__ out) {
+    double a = 0, b = 0;
+    for (int64_t i = threadIdx.x; i < nblocks; i += blockDim.x) { a += part[2 * i]; b += part[2 * i + 1]; }
+    a = warp_sum(a); b = warp_sum(b);
+    __shared__ double ra[32], rb[32];
+    if ((threadIdx.x & 31) == 0) { ra[threadIdx.x >> 5] = a; rb[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sa = 0, sb = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { sa += ra[w]; sb += rb[w]; }
+        out[0] = sa; out[1] = sb;
+    }
+}
+
+}  // namespace dlra

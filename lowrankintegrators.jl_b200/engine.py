@@ -1,0 +1,227 @@
+"""Thin object wrapper over a ``dlra_handle`` (include/dlra.h).  Holds no numerics: every method is one C-ABI call.
+Device memory handed to the engine is either a NumPy array (host path, ``*_host`` entry points) or a CUDA
+``torch.Tensor`` used purely as a device allocation (PyTorch is plumbing here, not the compute path)."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+try:  # torch is only needed for device-resident inputs and torch.distributed plumbing
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
+
+def _is_torch(x):
+    return torch is not None and isinstance(x, torch.Tensor)
+
+
+def colmajor_device(x):
+    """Return a CUDA fp64 tensor with column-major (Julia) layout, i.e. stride (1, ld); copies only if needed."""
+    assert _is_torch(x) and x.is_cuda and x.dtype == torch.float64 and x.dim() == 2
+    if x.shape[0] == 1 or x.stride(0) == 1:
+        if x.shape[1] == 1 or x.stride(1) >= x.shape[0]:
+            return x
+    return x.t().contiguous().t()
+
+
+def empty_colmajor(n, m, device):
+    return torch.empty((m, n), dtype=torch.float64, device=device).t()
+
+
+def _ptr_ld(x):
+    """(pointer, ld, is_host, keepalive) of a column-major fp64 matrix."""
+    if _is_torch(x):
+        if not x.is_cuda:
+            x = x.numpy()
+        else:
+            x = colmajor_device(x)
+            ld = x.stride(1) if x.shape[1] > 1 else x.shape[0]
+            return x.data_ptr(), int(ld), False, x
+    a = np.asarray(x, dtype=np.float64)
+    if a.ndim == 1:
+        a = a.reshape(-1, 1)
+    if not a.flags.f_contiguous:
+        a = np.asfortranarray(a)
+    return a.ctypes.data, int(a.shape[0]), True, a
+
+
+class Engine:
+    def __init__(self, n_local, m, r0, rmax=None, rank_adaptive=False, device=None, force_generic=False):
+        self.lib = L.load()
+        if torch is not None and torch.cuda.is_available():
+            device = torch.cuda.current_device() if device is None else device
+        elif device is None:
+            device = 0
+        self.device = int(device)
+        self.n, self.m = int(n_local), int(m)
+        rmax = r0 if rmax is None else rmax
+        flags = (L.RANK_ADAPTIVE if rank_adaptive else 0) | (L.FORCE_GENERIC if force_generic else 0)
+        h = L.handle_t()
+        rc = self.lib.dlra_create(self.device, self.n, self.m, int(r0), int(rmax), flags, C.byref(h))
+        if rc != L.OK:
+            raise L.DLRAError(rc, (self.lib.dlra_last_error(None) or b"").decode())
+        self.h = h
+        self.rmax = int(rmax)
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dlra_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        L.check(self.h, rc)
+
+    # -- multi-GPU ---------------------------------------------------------------------------------
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        buf = C.create_string_buffer(unique_id, 128)
+        self._ck(self.lib.dlra_comm_init(self.h, nranks, rank, buf))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        lib = L.load()
+        buf = C.create_string_buffer(128)
+        rc = lib.dlra_nccl_unique_id(buf)
+        if rc != L.OK:
+            raise L.DLRAError(rc, (lib.dlra_last_error(None) or b"").decode())
+        return buf.raw
+
+    # -- factors -----------------------------------------------------------------------------------
+    @property
+    def rank(self):
+        r = C.c_int()
+        self._ck(self.lib.dlra_get_rank(self.h, C.byref(r)))
+        return r.value
+
+    def set_factors(self, U, S, V):
+        r = int(np.shape(S)[0]) if not _is_torch(S) else int(S.shape[0])
+        pu, ldu, hu, ku = _ptr_ld(U)
+        ps, lds, hs, ks = _ptr_ld(S)
+        pv, ldv, hv, kv = _ptr_ld(V)
+        assert hu == hs == hv, "U, S, V must all live on the host or all on the device"
+        fn = self.lib.dlra_set_factors_host if hu else self.lib.dlra_set_factors
+        self._ck(fn(self.h, pu, ldu, ps, lds, pv, ldv, r))
+        if not hu:
+            self.sync()
+
+    def get_factors(self):
+        r = self.rank
+        U = np.empty((self.n, r), order="F")
+        S = np.empty((r, r), order="F")
+        V = np.empty((self.m, r), order="F")
+        rr = C.c_int()
+        self._ck(self.lib.dlra_get_factors_host(self.h, U.ctypes.data, self.n, S.ctypes.data, r, V.ctypes.data, self.m, C.byref(rr)))
+        return U, S, V
+
+    def get_factors_device(self):
+        r = self.rank
+        dev = torch.device("cuda", self.device)
+        U, S, V = empty_colmajor(self.n, r, dev), empty_colmajor(r, r, dev), empty_colmajor(self.m, r, dev)
+        rr = C.c_int()
+        self._ck(self.lib.dlra_get_factors(self.h, U.data_ptr(), self.n, S.data_ptr(), r, V.data_ptr(), self.m, C.byref(rr)))
+        return U, S, V
+
+    # -- data feed ---------------------------------------------------------------------------------
+    def data_init(self, A0):
+        p, ld, host, keep = _ptr_ld(A0)
+        fn = self.lib.dlra_data_init_host if host else self.lib.dlra_data_init
+        self._ck(fn(self.h, p, ld))
+        if host:
+            self.sync_copies = True
+        self._keep["prev"] = keep
+
+    def data_push(self, A, kind=L.DATA_SNAPSHOT):
+        p, ld, host, keep = _ptr_ld(A)
+        fn = self.lib.dlra_data_push_host if host else self.lib.dlra_data_push
+        self._ck(fn(self.h, p, ld, kind))
+        # borrowed device pointers must outlive the step after next: keep the last three alive
+        self._keep["cur3"] = (self._keep.get("cur3", ()) + (keep,))[-3:]
+
+    # -- DE problems -------------------------------------------------------------------------------
+    def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0):
+        self._ck(self.lib.dlra_set_substepper(self.h, flow, ode, nsub, abstol, reltol))
+
+    def rhs_set(self, A=None, B=None, G=None, H=None, D1=None, D2=None, c_had=0.0):
+        keep = []
+
+        def op(x):
+            if x is None:
+                return None
+            o = L.Operator()
+            if np.isscalar(x):
+                o.kind, o.scale = L.OP_IDENTITY_SCALED, float(x)
+                return o
+            if isinstance(x, tuple):  # CSR: (rowptr int64, colind int32, values fp64, shape) as CUDA tensors
+                rowptr, colind, values, shape = x
+                keep.extend([rowptr, colind, values])
+                o.kind, o.rows, o.cols = L.OP_CSR, shape[0], shape[1]
+                o.rowptr, o.colind, o.values, o.scale = rowptr.data_ptr(), colind.data_ptr(), values.data_ptr(), 1.0
+                return o
+            x = colmajor_device(x)
+            keep.append(x)
+            o.kind, o.rows, o.cols, o.dense, o.scale = L.OP_DENSE, x.shape[0], x.shape[1], x.data_ptr(), 1.0
+            o.ld = x.stride(1) if x.shape[1] > 1 else x.shape[0]
+            return o
+
+        ops = [op(A), op(B), op(D1), op(D2)]
+        refs = [C.byref(o) if o is not None else None for o in ops]
+        q = 0
+        pg = ph = None
+        ldg = ldh = 0
+        if G is not None:
+            G, H = colmajor_device(G), colmajor_device(H)
+            keep.extend([G, H])
+            q = G.shape[1]
+            pg, ldg = G.data_ptr(), (G.stride(1) if q > 1 else G.shape[0])
+            ph, ldh = H.data_ptr(), (H.stride(1) if q > 1 else H.shape[0])
+        self._ck(self.lib.dlra_rhs_set(self.h, refs[0], refs[1], pg, ldg, ph, ldh, q, refs[2], refs[3], float(c_had)))
+        self._keep["rhs"] = (keep, ops)
+
+    # -- steps -------------------------------------------------------------------------------------
+    def step_ksl(self, order, t=0.0, dt=1.0):
+        self._ck(self.lib.dlra_step_ksl(self.h, order, float(t), float(dt)))
+
+    def step_bug(self, t=0.0, dt=1.0):
+        self._ck(self.lib.dlra_step_bug(self.h, float(t), float(dt)))
+
+    def step_rabug(self, tol, rmax, t=0.0, dt=1.0):
+        rn, ch = C.c_int(), C.c_int()
+        self._ck(self.lib.dlra_step_rabug(self.h, float(t), float(dt), float(tol), int(min(rmax, 2 ** 62)), C.byref(rn), C.byref(ch)))
+        return rn.value, bool(ch.value)
+
+    def step_greedy(self, t=0.0, dt=1.0):
+        self._ck(self.lib.dlra_step_greedy(self.h, float(t), float(dt)))
+
+    def sync(self):
+        self._ck(self.lib.dlra_sync(self.h))
+
+    # -- diagnostics -------------------------------------------------------------------------------
+    def reconstruct_error(self, Yref):
+        p, ld, host, keep = _ptr_ld(Yref)
+        assert not host, "reconstruct_error takes a device matrix"
+        out = C.c_double()
+        self._ck(self.lib.dlra_reconstruct_error(self.h, p, ld, C.byref(out)))
+        return out.value
+
+    def reconstruct(self):
+        Y = empty_colmajor(self.n, self.m, torch.device("cuda", self.device))
+        self._ck(self.lib.dlra_reconstruct(self.h, Y.data_ptr(), self.n))
+        self.sync()
+        return Y
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.dlra_set_profiling(self.h, 1 if on else 0))
+
+    def stats(self, reset=False):
+        kl, pl = C.c_int64(), C.c_int64()
+        ms, by = C.c_double(), C.c_double()
+        self._ck(self.lib.dlra_stats(self.h, C.byref(kl), C.byref(pl), C.byref(ms), C.byref(by), 1 if reset else 0))
+        return {"kernel_launches": kl.value, "pass_launches": pl.value, "pass_ms": ms.value, "pass_bytes": by.value}
