@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — DLRA steps/sec of the per-step hot path (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus 1 --steps 50 --warmup 5            # this repo's engine (libdlra.so)
+  python bench.py --impl reference --steps 20 --warmup 3    # the reference's CPU algorithm (NumPy/OpenBLAS oracle;
+                                                            # the Julia reference itself cannot run: no Julia in the image)
+Workload (N=1): BASELINE.json configs[1] — MatrixDataProblem synthetic snapshot stream n=65536, m=4096, r=16,
+unconventional (BUG) integrator.  A "step" is one `step!` of the integrator on the next snapshot of a device-resident
+ring; the increment ΔA = A_{k+1} − A_k is formed on the fly inside both streaming passes (the reference's a2 work).
+N>1: every rank holds a cfg-2 sized row shard (n_local = 65536) of an N·65536 x 4096 problem (row sharding of SURVEY.md
+§8e: NCCL all-reduce of L/S/M, all-gather of the TSQR R factors); value counts shard-steps so N=1 equals configs[1].
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ROWS, M_COLS, RANK = 65536, 4096, 16
+METRIC, UNIT = "dlra_steps_per_sec", "steps/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def config_dict(n_gpus, impl):
+    return {
+        "workload": f"BASELINE configs[1]: MatrixDataProblem snapshot stream n={N_ROWS} (per GPU shard), m={M_COLS}, r={RANK}, "
+                    f"unconventional (BUG) integrator, snapshot ring of 3 resident in HBM, ΔA=A(k+1)-A(k) formed on the fly",
+        "n_local": N_ROWS, "n_global": N_ROWS * n_gpus, "m": M_COLS, "r": RANK, "integrator": "BUG",
+        "parallelism": f"row-shard x{n_gpus}" if n_gpus > 1 else "single GPU",
+        "l2_policy": "inputs larger than L2: each snapshot is 2 GiB vs 126 MB L2 (no flush needed)",
+        "init": "U0 block-orthonormal random, V0 orthonormal random, S0 = diag(2^-j) (identical for every arm)",
+        "impl": impl,
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the reference's algorithm (oracle restatement) on the host cores
+# ----------------------------------------------------------------------------------------------------
+def make_host_inputs(n, m, r, nsnap, seed=0):
+    rng = np.random.default_rng(seed)
+    snaps = [np.asfortranarray(rng.random((n, m)) - 0.5) for _ in range(nsnap)]
+    U0 = np.linalg.qr(rng.standard_normal((n, r)))[0]
+    V0 = np.linalg.qr(rng.standard_normal((m, r)))[0]
+    S0 = np.diag(2.0 ** -np.arange(r))
+    return snaps, U0, S0, V0
+
+
+def cpu_oracle_steps(n, m, r, steps, warmup):
+    """Times `steps` oracle BUG steps (reference step structure: 3 GEMM passes + elementwise ΔA formation) on an
+    n x m problem.  Returns seconds per step."""
+    from oracle import dlra_oracle as O
+    snaps, U0, S0, V0 = make_host_inputs(n, m, r, 3)
+    ring = [snaps[(k) % 3] for k in range(steps + warmup + 1)]
+    integ = O.init(O.MatrixDataProblem(ring, O.SVDLikeRepresentation(U0, S0, V0)), O.UnconventionalAlgorithm(), 1)
+    for _ in range(warmup):
+        O.step(integ)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.step(integ)
+    return (time.perf_counter() - t0) / steps
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frac = 8
+    n_s = N_ROWS // frac
+    sec = cpu_oracle_steps(n_s, M_COLS, RANK, args.steps, args.warmup) * frac   # BUG step cost is linear in n
+    value = 1.0 / sec
+    cores = blas_threads()
+    sample = (f"NumPy/OpenBLAS restatement of the reference BUG step (oracle/dlra_oracle.py), each timed step on a "
+              f"{n_s}x{M_COLS} row slice (1/{frac} of the workload), time scaled x{frac} (cost linear in n); "
+              f"Julia reference not runnable (no Julia in the image)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus, "reference-cpu-port"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    import lowrankintegrators.jl_b200 as lri
+    L = lri._lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    n, m, r = N_ROWS, M_COLS, RANK
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---- synthetic inputs (untimed): ring of 3 snapshots, SURVEY.md §8d recipe scaled by shard
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    R = 2 * r
+    P = torch.rand((n, R), generator=g, device=dev, dtype=torch.float64) * 2 - 1
+    gw = torch.Generator(device=dev)
+    gw.manual_seed(99)
+    Wm = torch.rand((m, R), generator=gw, device=dev, dtype=torch.float64) * 2 - 1
+    sig = 2.0 ** -torch.arange(R, device=dev, dtype=torch.float64)
+    om = torch.linspace(0.5, 2.0, R, device=dev, dtype=torch.float64)
+    snaps = []
+    for k in range(3):
+        A = lri.empty_colmajor(n, m, dev)
+        A.copy_((P * (sig * torch.cos(om * (0.1 * k)))) @ Wm.T)
+        A.add_(1e-6 * (torch.rand((n, m), generator=g, device=dev, dtype=torch.float64) * 2 - 1))
+        snaps.append(A)
+    U0 = torch.linalg.qr(torch.randn((n, r), generator=g, device=dev, dtype=torch.float64))[0] / np.sqrt(world)
+    V0 = torch.linalg.qr(torch.randn((m, r), generator=gw, device=dev, dtype=torch.float64))[0]
+    S0 = torch.diag(2.0 ** -torch.arange(r, device=dev, dtype=torch.float64))
+    del P
+
+    def make_engine():
+        eng = lri.Engine(n, m, r, rmax=r, device=local_rank)
+        if world > 1:
+            box = [lri.Engine.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            eng.comm_init(world, rank, box[0])
+        eng.set_factors(U0, S0, V0)
+        return eng
+
+    # ---- device-resident throughput ("value")
+    eng = make_engine()
+    eng.data_init(snaps[0])
+
+    def step(i):
+        eng.data_push(snaps[(i + 1) % 3], L.DATA_SNAPSHOT)
+        eng.step_bug()
+
+    for i in range(W):
+        step(i)
+    eng.sync()
+    eng.set_profiling(True)
+    eng.stats(reset=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    eng.event_record(0)
+    for i in range(W, W + K):
+        step(i)
+    eng.event_record(1)
+    ms_total = eng.event_elapsed_ms(0, 1)
+    eng.sync()
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    st = eng.stats()
+    brk = eng.pass_breakdown()
+    eng.set_profiling(False)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / K
+    value = world * 1e3 / ms_per_step
+    gpu_launches = int(st["kernel_launches"])
+
+    # ---- end to end through the public API with HOST snapshots (pinned), H2D + D2H inside the timed region
+    Ke = min(K, 20)
+    hsnaps = []
+    for A in snaps:
+        hp = torch.empty((m, n), dtype=torch.float64, pin_memory=True)
+        hp.copy_(A.t())
+        hsnaps.append(hp.numpy().T)   # F-contiguous n x m view of pinned memory
+    eng.close()
+    del snaps
+    torch.cuda.empty_cache()
+    eng = make_engine()
+    eng.data_init(hsnaps[0])
+    for i in range(2):
+        eng.data_push(hsnaps[(i + 1) % 3], L.DATA_SNAPSHOT)
+        eng.step_bug()
+        eng.get_factors()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    eng.data_push(hsnaps[(2 + 1) % 3], L.DATA_SNAPSHOT)
+    for i in range(2, 2 + Ke):
+        eng.step_bug()
+        if i + 1 < 2 + Ke:
+            eng.data_push(hsnaps[(i + 2) % 3], L.DATA_SNAPSHOT)   # H2D of the next snapshot overlaps this step
+        Uh, Sh, Vh = eng.get_factors()                            # update_sol!: deep copy of the step's result to the host
+    eng.sync()
+    torch.cuda.synchronize()
+    e2e_sec = (time.perf_counter() - t0) / Ke
+    if world > 1:
+        t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_sec = float(t.item())
+    e2e = {"value": world / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": n * m * 8, "d2h_bytes_per_step": (n * r + r * r + m * r) * 8,
+           "steps": Ke, "note": "dlra_data_push_host (pinned host snapshot) + dlra_step_bug + dlra_get_factors_host per step"}
+    eng.close()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: the fused K+L streaming pass (snapshot mode reads A(k+1) and A(k))
+    peaks, peak_src = measured_peaks()
+    fk = brk["fused_KL"]
+    roof = None
+    if fk["launches"] > 0 and fk["ms"] > 0:
+        achieved = fk["bytes"] / (fk["ms"] * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_pass_traffic.json")) as f:
+                traffic = json.load(f).get("fused_KL_diff_bytes_per_launch")
+        except Exception:
+            pass
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": traffic, "kernel": "pass_kernel<16,K,L,DIFF> (fused K+L, A(k+1)-A(k) on the fly)",
+                "bytes_per_launch": fk["bytes"] / fk["launches"], "ms_per_launch": fk["ms"] / fk["launches"],
+                "fp64_tflops": fk["flops"] / (fk["ms"] * 1e-3) / 1e12, "peak_source": peak_src,
+                "other_passes": {k: {"gbs": (v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else None,
+                                     "ms_per_launch": (v["ms"] / v["launches"]) if v["launches"] else None,
+                                     "launches": v["launches"]} for k, v in brk.items() if k != "fused_KL"},
+                "pass_share_of_step": st["pass_ms"] / ms_total}
+
+    # ---- CPU baseline (rank 0, N=1 only): 2 oracle BUG steps at the full cfg-2 size
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sec = cpu_oracle_steps(n, m, r, 2, 1)
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+               "sample": f"2 timed + 1 warm-up BUG steps of oracle/dlra_oracle.py (NumPy/OpenBLAS restatement of the reference step) at the full {n}x{m}, r={r} size"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(world, "libdlra.so"), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": gpu_launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -155,6 +155,12 @@ int dlra_reconstruct(dlra_handle h, double* Y, int64_t ld);
 int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass_launches, double* pass_ms_total,
                double* pass_bytes_total, int reset);
 int dlra_set_profiling(dlra_handle h, int time_passes);
+/* per-kind breakdown of the timed contraction launches since the last reset:
+ * index 0 = fused K+L pass, 1 = K-only pass (also the first half of the S pass), 2 = L-only pass */
+int dlra_pass_breakdown(dlra_handle h, int64_t launches[3], double ms[3], double bytes[3], double flops[3]);
+/* CUDA events on the ENGINE's stream (torch.cuda.Event only sees torch's streams): slots 0..7 */
+int dlra_event_record(dlra_handle h, int slot);
+int dlra_event_elapsed_ms(dlra_handle h, int slot_begin, int slot_end, double* ms); /* synchronises on slot_end */
 
 #ifdef __cplusplus
 }

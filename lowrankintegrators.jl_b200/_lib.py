@@ -57,6 +57,9 @@ SIGNATURES = {
     "dlra_reconstruct": (C.c_int, [handle_t, C.c_void_p, C.c_int64]),
     "dlra_stats": (C.c_int, [handle_t, c_i64_p, c_i64_p, c_double_p, c_double_p, C.c_int]),
     "dlra_set_profiling": (C.c_int, [handle_t, C.c_int]),
+    "dlra_pass_breakdown": (C.c_int, [handle_t, c_i64_p, c_double_p, c_double_p, c_double_p]),
+    "dlra_event_record": (C.c_int, [handle_t, C.c_int]),
+    "dlra_event_elapsed_ms": (C.c_int, [handle_t, C.c_int, C.c_int, c_double_p]),
 }
 
 _lib = None

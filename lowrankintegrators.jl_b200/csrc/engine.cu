@@ -96,6 +96,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     for (int i = 0; i < 3; ++i) { if (h->own[i]) cudaFree(h->own[i]); cudaEventDestroy(h->own_free[i]); cudaEventDestroy(h->own_ready[i]); }
     h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release();
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (int i = 0; i < 8; ++i) if (h->user_events[i]) cudaEventDestroy(h->user_events[i]);
     de_release(h);
     cudaStreamDestroy(h->cx.stream); cudaStreamDestroy(h->copy_stream);
     delete h;
@@ -630,17 +631,55 @@ extern "C" int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass
                           double* pass_bytes_total, int reset) {
     DLRA_API_BEGIN(h)
     DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));
-    for (auto& pr : h->pass_events) {
+    for (size_t i = 0; i < h->pass_events.size(); ++i) {
+        auto& pr = h->pass_events[i];
         float ms = 0.f;
         DLRA_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
         h->pass_ms += ms;
+        h->kind_ms[h->pass_event_kind[i]] += ms;
         cudaEventDestroy(pr.first); cudaEventDestroy(pr.second);
     }
     h->pass_events.clear();
+    h->pass_event_kind.clear();
     if (kernel_launches) *kernel_launches = h->cx.launches;
     if (pass_launches) *pass_launches = h->pass_launches;
     if (pass_ms_total) *pass_ms_total = h->pass_ms;
     if (pass_bytes_total) *pass_bytes_total = h->pass_bytes;
-    if (reset) { h->cx.launches = 0; h->pass_launches = 0; h->pass_ms = 0.0; h->pass_bytes = 0.0; }
+    if (reset) {
+        h->cx.launches = 0; h->pass_launches = 0; h->pass_ms = 0.0; h->pass_bytes = 0.0;
+        for (int i = 0; i < 3; ++i) { h->kind_launches[i] = 0; h->kind_ms[i] = 0; h->kind_bytes[i] = 0; h->kind_flops[i] = 0; }
+    }
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_pass_breakdown(dlra_handle h, int64_t launches[3], double ms[3], double bytes[3], double flops[3]) {
+    DLRA_API_BEGIN(h)
+    int64_t a, b; double c, d;
+    int rc = dlra_stats(h, &a, &b, &c, &d, 0);   // folds pending events into the per-kind sums
+    DLRA_REQUIRE(rc == DLRA_OK, "stats failed");
+    for (int i = 0; i < 3; ++i) {
+        if (launches) launches[i] = h->kind_launches[i];
+        if (ms) ms[i] = h->kind_ms[i];
+        if (bytes) bytes[i] = h->kind_bytes[i];
+        if (flops) flops[i] = h->kind_flops[i];
+    }
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_event_record(dlra_handle h, int slot) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(slot >= 0 && slot < 8, "event slot out of range");
+    if (!h->user_events[slot]) DLRA_CUDA(cudaEventCreate(&h->user_events[slot]));
+    DLRA_CUDA(cudaEventRecord(h->user_events[slot], h->cx.stream));
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_event_elapsed_ms(dlra_handle h, int a, int b, double* ms) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(a >= 0 && a < 8 && b >= 0 && b < 8 && ms && h->user_events[a] && h->user_events[b], "bad event slots");
+    DLRA_CUDA(cudaEventSynchronize(h->user_events[b]));
+    float f = 0.f;
+    DLRA_CUDA(cudaEventElapsedTime(&f, h->user_events[a], h->user_events[b]));
+    *ms = f;
     DLRA_API_END(h)
 }

@@ -90,6 +90,32 @@ struct dlra_engine {
     // profiling of the dominant contraction kernels
     bool time_passes = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pass_events;
+    std::vector<int> pass_event_kind;
     int64_t pass_launches = 0;
     double pass_bytes = 0.0, pass_ms = 0.0;
+    int64_t kind_launches[3] = {0, 0, 0};
+    double kind_ms[3] = {0, 0, 0}, kind_bytes[3] = {0, 0, 0}, kind_flops[3] = {0, 0, 0};
+    cudaEvent_t user_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
+
+namespace dlra {
+inline void pass_timer_begin(dlra_engine* e, double bytes, int kind = 1, double flops = 0.0) {
+    e->pass_launches++;
+    e->pass_bytes += bytes;
+    e->kind_launches[kind]++;
+    e->kind_bytes[kind] += bytes;
+    e->kind_flops[kind] += flops;
+    if (!e->time_passes) return;
+    e->pass_event_kind.push_back(kind);
+    cudaEvent_t a, b;
+    DLRA_CUDA(cudaEventCreate(&a));
+    DLRA_CUDA(cudaEventCreate(&b));
+    DLRA_CUDA(cudaEventRecord(a, e->cx.stream));
+    e->pass_events.emplace_back(a, b);
+}
+inline void pass_timer_end(dlra_engine* e) {
+    if (!e->time_passes) return;
+    DLRA_CUDA(cudaEventRecord(e->pass_events.back().second, e->cx.stream));
+}
+
+}  // namespace dlra

@@ -1,8 +1,401 @@
-// placeholder until the TMA + DMMA streaming kernels land
+// Fused streaming contraction over the dense increment ΔA (n x m, column-major) for sm_100a:
+//     K[rows, c] += Σ_j ΔA[rows, j]·Vf[j, c]          (K-use, complete per row panel)
+//     Lpart[panel][j, c] = Σ_{rows∈panel} ΔA[rows, j]·Uf[rows, c]   (L-use, reduced over panels afterwards)
+// in ONE read of ΔA.  ΔA = A − Aprev is formed in shared memory when a previous snapshot is given
+// (`Δy .= ycurr - yprev`, projector_splitting.jl:119-121), so the increment never exists in HBM.
+//
+// Mapping to the hardware
+//  * one persistent CTA per SM owns row panels of 64·nsub rows and sweeps all column tiles (32 columns);
+//    a producer warp streams 64 x 32 stages through a ring with TMA (cp.async.bulk.tensor.2d, SASS UTMALDG)
+//    + mbarrier full/empty pairs; ΔA tiles carry an L2 evict_first hint, the factor tiles evict_last.
+//  * tiles land as 16-row boxes in SWIZZLE_128B layout; the MMA row blocks use the row permutation
+//    {0,1,8,9,2,3,10,11}+4b so that BOTH fragment patterns (8 rows x 4 cols for the K-use, 4 rows x 8 cols for the
+//    L-use) read shared memory bank-conflict free.
+//  * math runs on the fp64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — tcgen05/UMMA has no f64 kind).
+//    Each of the 8 consumer warps owns 8 rows of every stage for both uses; K accumulators stay in registers
+//    for the whole panel, L accumulators for one column tile, then an in-CTA reduction over the 8 warps and a
+//    deterministic fixed-order reduction over panels (no atomics).
+//  * r is processed in chunks of RT in {8, 16} factor columns: at RT = 16 the pass is already fp64-bound
+//    (AI = r/2 flop/B vs a ridge of ~5.6), so wider ranks re-stream ΔA per chunk at no cost in time.
 #pragma once
 #include "engine.cuh"
+
 namespace dlra {
-inline bool tma_pass_supported(int64_t, int64_t, const Delta&) { return false; }
-inline void tma_pass_KL(dlra_engine*, const Delta&, int, const double*, int64_t, const double*, int64_t, double*, int64_t, double*, int64_t) {}
-inline void tma_pass_S(dlra_engine*, const Delta&, int, int, const double*, int64_t, const double*, int64_t, double*, int64_t) {}
+
+constexpr int PT_SI = 64;        // rows per stage
+constexpr int PT_TJ = 32;        // columns per stage
+constexpr int PT_NSUB_MAX = 7;   // stages (row sub-tiles) per panel held in K accumulators
+constexpr int PT_CONSUMERS = 8;  // consumer warps
+constexpr int PT_THREADS = (PT_CONSUMERS + 1) * 32;
+constexpr int PT_TBYTES = PT_SI * PT_TJ * 8;  // 16 KB
+constexpr int PT_BOXBYTES = 16 * PT_TJ * 8;   // 4 KB: one 16-row box
+
+struct PassParams {
+    int64_t n, m;
+    int rc;          // valid factor columns in this chunk (<= RT)
+    int nsub;        // row sub-tiles per panel
+    int npanels;
+    int ntj;         // column tiles
+    double* K; int64_t ldk;       // K-use output (+=), may be null
+    const double* Kin;            // unused
+    double* Lpart; int64_t ldlp;  // [npanels][ldlp x RT] partial L (ldlp >= m), may be null
+};
+
+template <int RT, bool DO_K, bool DO_L, bool DIFF>
+struct PassSmem {
+    static constexpr int VBYTES = DO_K ? PT_TJ * RT * 8 : 0;
+    static constexpr int STAGE_BYTES = ((PT_TBYTES * (DIFF ? 2 : 1) + VBYTES + 1023) / 1024) * 1024;
+    static constexpr int UBOX_BYTES = 16 * RT * 8;
+    static constexpr int UPANEL_BYTES = DO_L ? PT_NSUB_MAX * 4 * UBOX_BYTES : 0;
+    static constexpr int LRED_BYTES = DO_L ? PT_CONSUMERS * PT_TJ * RT * 8 : 0;
+    static constexpr int BUDGET = 225 * 1024;
+    static constexpr int NST_RAW = (BUDGET - UPANEL_BYTES - LRED_BYTES - 1024) / STAGE_BYTES;
+    static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
+    static constexpr int TOTAL = NST * STAGE_BYTES + UPANEL_BYTES + LRED_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int RT, bool DO_K, bool DO_L, bool DIFF>
+__global__ void __launch_bounds__(PT_THREADS, 1)
+pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapP,
+            const __grid_constant__ CUtensorMap mapU, const __grid_constant__ CUtensorMap mapV, const PassParams prm) {
+    using SM = PassSmem<RT, DO_K, DO_L, DIFF>;
+    constexpr int NST = SM::NST;
+    constexpr int NB = RT / 8;
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte aligned carve-up (SWIZZLE_128B boxes need it)
+    unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char* stages = base;
+    unsigned char* upanel = stages + (size_t)NST * SM::STAGE_BYTES;
+    double* lred = reinterpret_cast<double*>(upanel + SM::UPANEL_BYTES);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(lred) + SM::LRED_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NST;
+    uint64_t* panel_done = bars + 2 * NST;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], PT_CONSUMERS); }
+        mbar_init(panel_done, PT_CONSUMERS);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int nsub = prm.nsub;
+    if (warp == PT_CONSUMERS) {
+        // ------------------------------ producer: one elected lane drives the TMA engine -------------------
+        if (lane == 0) {
+            prefetch_tmap(&mapA);
+            if (DIFF) prefetch_tmap(&mapP);
+            if (DO_L) prefetch_tmap(&mapU);
+            if (DO_K) prefetch_tmap(&mapV);
+            const uint64_t pol_stream = policy_evict_first();
+            const uint64_t pol_keep = policy_evict_last();
+            int stage = 0; uint32_t phase = 0; uint32_t pd_phase = 0; bool first_panel = true;
+            for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
+                if (!first_panel) { mbar_wait(panel_done, pd_phase); pd_phase ^= 1; }  // U panel region is free again
+                first_panel = false;
+                const int row0 = panel * nsub * PT_SI;
+                for (int jt = 0; jt < prm.ntj; ++jt) {
+                    for (int s = 0; s < nsub; ++s) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        uint32_t bytes = PT_TBYTES * (DIFF ? 2 : 1);
+                        if (DO_K && s == 0) bytes += SM::VBYTES;
+                        if (DO_L && jt == 0) bytes += 4 * SM::UBOX_BYTES;
+                        mbar_expect_tx(&full[stage], bytes);
+                        unsigned char* sb = stages + (size_t)stage * SM::STAGE_BYTES;
+                        const int r = row0 + s * PT_SI;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            tma_load_2d(sb + b * PT_BOXBYTES, &mapA, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
+                            if (DIFF) tma_load_2d(sb + PT_TBYTES + b * PT_BOXBYTES, &mapP, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
+                        }
+                        if (DO_K && s == 0) tma_load_2d(sb + PT_TBYTES * (DIFF ? 2 : 1), &mapV, jt * PT_TJ, 0, &full[stage], pol_keep);
+                        if (DO_L && jt == 0) {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b)
+                                tma_load_2d(upanel + (size_t)(s * 4 + b) * SM::UBOX_BYTES, &mapU, r + 16 * b, 0, &full[stage], pol_keep);
+                        }
+                        if (++stage == NST) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumers: 8 warps, DMMA ------------------------------------------
+    const int g = lane >> 2, k = lane & 3;
+    const int wbox = warp >> 1, wblk = warp & 1;
+    // K-use fragment (8 rows x 4 cols): row = prow(wblk, g), col = 4*ks + k
+    const int prow = (g & 1) + ((g >> 1) & 1) * 8 + (g >> 2) * 2 + wblk * 4;
+    const uint32_t offKe = k * 128 + (((prow >> 1) ^ k) << 4) + (prow & 1) * 8;          // even ks
+    const uint32_t offKo = k * 128 + (((prow >> 1) ^ (4 + k)) << 4) + (prow & 1) * 8;    // odd ks
+    // L-use fragment (4 rows x 8 cols): row = lrow(kk, k), col = 8*cb + g
+    uint32_t offL[2];
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        const int lrow = (k & 1) + ((k >> 1) & 1) * 8 + 2 * kk + 4 * wblk;
+        offL[kk] = g * 128 + (((lrow >> 1) ^ g) << 4) + (lrow & 1) * 8;
+    }
+    // rows of this thread's C fragments inside a stage
+    const int crow = wbox * 16 + prow;
+
+    int stage = 0; uint32_t phase = 0;
+    for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
+        const int64_t row0 = (int64_t)panel * nsub * PT_SI;
+        double kacc[PT_NSUB_MAX][NB][2];
+        if (DO_K) {
+#pragma unroll
+            for (int s = 0; s < PT_NSUB_MAX; ++s)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) { kacc[s][nb][0] = 0.0; kacc[s][nb][1] = 0.0; }
+        }
+        for (int jt = 0; jt < prm.ntj; ++jt) {
+            double lacc[4][NB][2];
+            double vf[8][NB];
+            if (DO_L) {
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) { lacc[cb][nb][0] = 0.0; lacc[cb][nb][1] = 0.0; }
+            }
+#pragma unroll
+            for (int s = 0; s < PT_NSUB_MAX; ++s) {
+                if (s < nsub) {
+                    mbar_wait(&full[stage], phase);
+                    unsigned char* sb = stages + (size_t)stage * SM::STAGE_BYTES;
+                    unsigned char* tb = sb + wbox * PT_BOXBYTES;
+                    if (DO_K && s == 0) {
+                        // B fragments of the K-use for this column tile: Vf[4*ks + k][8*nb + g], V tile is dense [c][32]
+                        const double* vt = reinterpret_cast<const double*>(sb + PT_TBYTES * (DIFF ? 2 : 1));
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks)
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) vf[ks][nb] = vt[(8 * nb + g) * PT_TJ + 4 * ks + k];
+                    }
+                    if (DIFF) {
+                        // ΔA = A − Aprev on this warp's own 8 rows x 32 cols (rows come in adjacent pairs = 16-byte chunks)
+                        unsigned char* pb = tb + PT_TBYTES;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int ch = lane + 32 * i;           // 128 chunks: column = ch >> 2, pair index = ch & 3
+                            const int col = ch >> 2, pr = ch & 3;   // pair rows: {0,1},{8,9},{2,3},{10,11} (+4*wblk)
+                            const int rowp = ((pr & 1) * 8 + (pr >> 1) * 2 + 4 * wblk) >> 1;   // row >> 1
+                            const uint32_t off = col * 128 + ((rowp ^ (col & 7)) << 4);
+                            double2 a = *reinterpret_cast<double2*>(tb + off);
+                            const double2 p = *reinterpret_cast<const double2*>(pb + off);
+                            a.x -= p.x; a.y -= p.y;
+                            *reinterpret_cast<double2*>(tb + off) = a;
+                        }
+                        __syncwarp();
+                    }
+                    if (DO_K) {
+#pragma unroll
+                        for (int ks = 0; ks < 8; ++ks) {
+                            const double a = *reinterpret_cast<const double*>(tb + ((ks & 1) ? offKo : offKe) + ks * 512);
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) dmma884(kacc[s][nb][0], kacc[s][nb][1], a, vf[ks][nb]);
+                        }
+                    }
+                    if (DO_L) {
+                        const unsigned char* ub = upanel + (size_t)(s * 4 + wbox) * SM::UBOX_BYTES;
+#pragma unroll
+                        for (int kk = 0; kk < 2; ++kk) {
+                            double uf[NB];
+#pragma unroll
+                            for (int nb = 0; nb < NB; ++nb) uf[nb] = *reinterpret_cast<const double*>(ub + offL[kk] + nb * 1024);
+#pragma unroll
+                            for (int cb = 0; cb < 4; ++cb) {
+                                const double a = *reinterpret_cast<const double*>(tb + offL[kk] + cb * 1024);
+#pragma unroll
+                                for (int nb = 0; nb < NB; ++nb) dmma884(lacc[cb][nb][0], lacc[cb][nb][1], a, uf[nb]);
+                            }
+                        }
+                    }
+                    if (DIFF) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (DO_L) {
+                // in-CTA reduction of the 8 warps' partial L tiles, then one coalesced store of the panel partial
+                double* mine = lred + (size_t)warp * PT_TJ * RT;
+#pragma unroll
+                for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        mine[(8 * nb + 2 * k) * PT_TJ + 8 * cb + g] = lacc[cb][nb][0];
+                        mine[(8 * nb + 2 * k + 1) * PT_TJ + 8 * cb + g] = lacc[cb][nb][1];
+                    }
+                asm volatile("bar.sync 1, %0;" ::"n"(PT_CONSUMERS * 32) : "memory");
+                double* lp = prm.Lpart + (size_t)panel * prm.ldlp * RT;
+#pragma unroll
+                for (int i = 0; i < (PT_TJ * RT) / (PT_CONSUMERS * 32); ++i) {
+                    const int e = tid + i * PT_CONSUMERS * 32;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int w = 0; w < PT_CONSUMERS; ++w) sum += lred[(size_t)w * PT_TJ * RT + e];
+                    const int c = e / PT_TJ, j = e % PT_TJ;
+                    const int64_t col = (int64_t)jt * PT_TJ + j;
+                    if (col < prm.m) lp[col + (int64_t)c * prm.ldlp] = sum;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(PT_CONSUMERS * 32) : "memory");
+            }
+        }
+        if (DO_K) {
+#pragma unroll
+            for (int s = 0; s < PT_NSUB_MAX; ++s) {
+                if (s < nsub) {
+                    const int64_t row = row0 + s * PT_SI + crow;
+                    if (row < prm.n) {
+#pragma unroll
+                        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int c = 8 * nb + 2 * k + e;
+                                if (c < prm.rc) prm.K[row + (int64_t)c * prm.ldk] += kacc[s][nb][e];
+                            }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(panel_done);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        DLRA_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (q != cudaDriverEntryPointSuccess || !p) throw CudaError(2, "cuTensorMapEncodeTiled not available from the driver");
+        fn = (PFN_encodeTiled)p;
+    }
+    return fn;
+}
+
+inline CUtensorMap make_map_2d(const double* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int box_cols, bool swizzle128) {
+    CUtensorMap m;
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {(cuuint32_t)box_rows, (cuuint32_t)box_cols};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult rc = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, estr,
+                                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw CudaError(2, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)rc) + ")");
+    return m;
+}
+
+inline bool tma_ok(const double* p, int64_t ld) { return p && (((uintptr_t)p) & 15) == 0 && (ld % 2) == 0; }
+
+inline bool tma_pass_supported(int64_t n, int64_t m, const Delta& d) {
+    if (n < 64 || m < 8 || (n % 2) != 0 || (m % 2) != 0) return false;  // TMA strides must be multiples of 16 bytes
+    if (n >= ((int64_t)1 << 31) || m >= ((int64_t)1 << 31)) return false;
+    if (!tma_ok(d.A, d.lda)) return false;
+    if (d.Aprev && !tma_ok(d.Aprev, d.ldap)) return false;
+    return true;
+}
+
+inline int choose_nsub(int64_t n, int num_sms) {
+    const int64_t subtiles = cdiv(n, PT_SI);
+    int best = 1; double best_cost = 1e300;
+    for (int ns = 1; ns <= PT_NSUB_MAX; ++ns) {
+        const int64_t panels = cdiv(subtiles, ns);
+        const double cost = (double)cdiv(panels, num_sms) * ns + 0.02 * (double)panels / num_sms;  // makespan + partial-L overhead
+        if (cost < best_cost - 1e-12) { best_cost = cost; best = ns; }
+    }
+    return best;
+}
+
+template <int RT, bool DO_K, bool DO_L, bool DIFF>
+inline void launch_pass(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
+                        double* K, int64_t ldk, double* Lpart, int64_t ldlp, int nsub, int npanels) {
+    using SM = PassSmem<RT, DO_K, DO_L, DIFF>;
+    static_assert(SM::NST >= 2, "pipeline needs at least two stages");
+    auto kern = pass_kernel<RT, DO_K, DO_L, DIFF>;
+    static bool attr = false;
+    if (!attr) {
+        DLRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+        attr = true;
+    }
+    CUtensorMap mapA = make_map_2d(d.A, e->n, e->m, d.lda, 16, PT_TJ, true);
+    CUtensorMap mapP = DIFF ? make_map_2d(d.Aprev, e->n, e->m, d.ldap, 16, PT_TJ, true) : mapA;
+    CUtensorMap mapU = DO_L ? make_map_2d(Uf, e->n, rc, ldu, 16, RT, true) : mapA;
+    CUtensorMap mapV = DO_K ? make_map_2d(Vf, e->m, rc, ldv, PT_TJ, RT, false) : mapA;
+    PassParams prm;
+    prm.n = e->n; prm.m = e->m; prm.rc = rc; prm.nsub = nsub; prm.npanels = npanels; prm.ntj = (int)cdiv(e->m, PT_TJ);
+    prm.K = K; prm.ldk = ldk; prm.Kin = nullptr; prm.Lpart = Lpart; prm.ldlp = ldlp;
+    const int grid = std::min(npanels, e->cx.num_sms);
+    const double bytes = (double)e->n * (double)e->m * 8.0 * (DIFF ? 2.0 : 1.0);
+    const double flops = 2.0 * (double)e->n * (double)e->m * rc * ((DO_K ? 1 : 0) + (DO_L ? 1 : 0));
+    pass_timer_begin(e, bytes, (DO_K && DO_L) ? 0 : (DO_K ? 1 : 2), flops);
+    kern<<<grid, PT_THREADS, SM::TOTAL, e->cx.stream>>>(mapA, mapP, mapU, mapV, prm);
+    pass_timer_end(e);
+    e->cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
+template <int RT>
+inline void launch_pass_rt(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
+                           double* K, int64_t ldk, double* Lpart, int64_t ldlp, int nsub, int npanels) {
+    const bool dk = K != nullptr, dl = Lpart != nullptr, df = d.Aprev != nullptr;
+#define DLRA_PASS_CASE(a, b, c) \
+    if (dk == a && dl == b && df == c) return launch_pass<RT, a, b, c>(e, d, rc, Vf, ldv, Uf, ldu, K, ldk, Lpart, ldlp, nsub, npanels);
+    DLRA_PASS_CASE(true, true, false)
+    DLRA_PASS_CASE(true, true, true)
+    DLRA_PASS_CASE(true, false, false)
+    DLRA_PASS_CASE(true, false, true)
+    DLRA_PASS_CASE(false, true, false)
+    DLRA_PASS_CASE(false, true, true)
+#undef DLRA_PASS_CASE
+}
+
+// K (n x r) += ΔA·Vf and/or Lout (m x r, ldl) = ΔAᵀ·Uf, r processed in chunks of 16 (8 for a narrow tail)
+inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
+                        double* K, int64_t ldk, double* Lout, int64_t ldl) {
+    // factor operands must satisfy the TMA alignment rules too; otherwise stage them through aligned scratch
+    DLRA_REQUIRE((!K || tma_ok(Vf, ldv)) && (!Lout || tma_ok(Uf, ldu)), "factor buffers must be 16-byte aligned with even ld");
+    const int nsub = choose_nsub(e->n, e->cx.num_sms);
+    const int npanels = (int)cdiv(cdiv(e->n, PT_SI), nsub);
+    const int64_t ldlp = round_up(e->m, 2);
+    if (Lout) e->part.ensure((int64_t)npanels * ldlp * 16, e->cx.stream);
+    for (int c0 = 0; c0 < r; c0 += 16) {
+        const int rc = std::min(16, r - c0);
+        double* Kc = K ? K + (int64_t)c0 * ldk : nullptr;
+        double* Lp = Lout ? e->part.p : nullptr;
+        const double* Vc = Vf ? Vf + (int64_t)c0 * ldv : nullptr;
+        const double* Uc = Uf ? Uf + (int64_t)c0 * ldu : nullptr;
+        if (rc <= 8) {
+            launch_pass_rt<8>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
+            if (Lout) reduce_parts(e->cx, (int)e->m, rc, npanels, Lp, ldlp, ldlp * 8, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
+        } else {
+            launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
+            if (Lout) reduce_parts(e->cx, (int)e->m, rc, npanels, Lp, ldlp, ldlp * 16, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
+        }
+    }
+}
+
+// Sout (p x q) = Lfᵀ·(ΔA·Rf): the K-use streams W = ΔA·Rf (n x q, 8·n·q bytes — <1% of the ΔA traffic) and a
+// tall-skinny Gram product folds it with Lf.
+inline void tma_pass_S(dlra_engine* e, const Delta& d, int p, int q, const double* Lf, int64_t ldlf, const double* Rf, int64_t ldrf,
+                       double* Sout, int64_t lds) {
+    Ctx& cx = e->cx;
+    e->nscr.ensure(e->n * (int64_t)q, cx.stream);
+    DLRA_CUDA(cudaMemsetAsync(e->nscr.p, 0, (size_t)e->n * q * 8, cx.stream));
+    tma_pass_KL(e, d, q, Rf, ldrf, nullptr, 0, e->nscr.p, e->n, nullptr, 0);
+    e->gws.ensure(gemm_tn_ws(cx, e->n, p, q), cx.stream);
+    gemm_tn(cx, e->n, p, q, Lf, ldlf, nullptr, 0, e->nscr.p, e->n, Sout, lds, 1.0, 0.0, e->gws.p);
+}
+
 }  // namespace dlra

@@ -1,7 +1,7 @@
 // The K/L/S contractions over the dense increment ΔA — `u .+= sign*left'*Δy*right`
 // (data_integrator.jl:13-16) — as two fused streaming passes per step:
 //   pass_KL : K += ΔA·Vf  (n x r, complete rows)   and/or   Lout = ΔAᵀ·Uf  (m x r, reduced over row panels)
-//   pass_S  : Sout = Lfᵀ·ΔA·Rf   (p x q core; the n x q intermediate never leaves the SM on the fast path)
+//   pass_S  : Sout = Lfᵀ·ΔA·Rf   (p x q core: K-use W = ΔA·Rf, then a tall-skinny Gram product Lfᵀ·W)
 // ΔA is either a pre-differenced increment or formed on the fly as A − Aprev (the reference's
 // `Δy .= ycurr - yprev`, projector_splitting.jl:119-121) so no n x m temporary is ever written.
 // Dispatch: TMA + DMMA kernels (pass_tma.cuh) when the shape/alignment allows, else the generic GEMMs.
@@ -11,21 +11,6 @@
 
 namespace dlra {
 
-inline void pass_timer_begin(dlra_engine* e, double bytes) {
-    e->pass_launches++;
-    e->pass_bytes += bytes;
-    if (!e->time_passes) return;
-    cudaEvent_t a, b;
-    DLRA_CUDA(cudaEventCreate(&a));
-    DLRA_CUDA(cudaEventCreate(&b));
-    DLRA_CUDA(cudaEventRecord(a, e->cx.stream));
-    e->pass_events.emplace_back(a, b);
-}
-inline void pass_timer_end(dlra_engine* e) {
-    if (!e->time_passes) return;
-    DLRA_CUDA(cudaEventRecord(e->pass_events.back().second, e->cx.stream));
-}
-
 inline double delta_bytes(const dlra_engine* e, const Delta& d) { return (double)e->n * (double)e->m * 8.0 * (d.Aprev ? 2.0 : 1.0); }
 
 // K (n x r, ldk) += ΔA·Vf  if K != nullptr ;  Lout (m x r, ldl) = ΔAᵀ·Uf (this rank's rows only) if Lout != nullptr
@@ -33,19 +18,17 @@ inline void pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int
                     double* K, int64_t ldk, double* Lout, int64_t ldl) {
     Ctx& cx = e->cx;
     if (!(e->flags & DLRA_FORCE_GENERIC) && tma_pass_supported(e->n, e->m, d)) {
-        pass_timer_begin(e, delta_bytes(e, d));
-        tma_pass_KL(e, d, r, Vf, ldv, Uf, ldu, K, ldk, Lout, ldl);
-        pass_timer_end(e);
+        tma_pass_KL(e, d, r, Vf, ldv, Uf, ldu, K, ldk, Lout, ldl);   // timed per kernel launch inside
         return;
     }
     if (K) {
-        pass_timer_begin(e, delta_bytes(e, d));
+        pass_timer_begin(e, delta_bytes(e, d), 1, 2.0 * (double)e->n * (double)e->m * r);
         gemm_nn(cx, e->n, (int)e->m, r, d.A, d.lda, d.Aprev, d.ldap, Vf, ldv, false, K, ldk, 1.0, 1.0);
         pass_timer_end(e);
     }
     if (Lout) {
         e->gws.ensure(gemm_tn_ws(cx, e->n, (int)e->m, r), cx.stream);
-        pass_timer_begin(e, delta_bytes(e, d));
+        pass_timer_begin(e, delta_bytes(e, d), 2, 2.0 * (double)e->n * (double)e->m * r);
         gemm_tn(cx, e->n, (int)e->m, r, d.A, d.lda, d.Aprev, d.ldap, Uf, ldu, Lout, ldl, 1.0, 0.0, e->gws.p);
         pass_timer_end(e);
     }
@@ -56,13 +39,11 @@ inline void pass_S(dlra_engine* e, const Delta& d, int p, int q, const double* L
                    double* Sout, int64_t lds) {
     Ctx& cx = e->cx;
     if (!(e->flags & DLRA_FORCE_GENERIC) && tma_pass_supported(e->n, e->m, d)) {
-        pass_timer_begin(e, delta_bytes(e, d));
         tma_pass_S(e, d, p, q, Lf, ldlf, Rf, ldrf, Sout, lds);
-        pass_timer_end(e);
         return;
     }
     e->nscr.ensure(e->n * (int64_t)q, cx.stream);
-    pass_timer_begin(e, delta_bytes(e, d));
+    pass_timer_begin(e, delta_bytes(e, d), 1, 2.0 * (double)e->n * (double)e->m * q);
     gemm_nn(cx, e->n, (int)e->m, q, d.A, d.lda, d.Aprev, d.ldap, Rf, ldrf, false, e->nscr.p, e->n, 1.0, 0.0);
     pass_timer_end(e);
     e->gws.ensure(gemm_tn_ws(cx, e->n, p, q), cx.stream);

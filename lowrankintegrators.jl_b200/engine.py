@@ -225,3 +225,18 @@ class Engine:
         ms, by = C.c_double(), C.c_double()
         self._ck(self.lib.dlra_stats(self.h, C.byref(kl), C.byref(pl), C.byref(ms), C.byref(by), 1 if reset else 0))
         return {"kernel_launches": kl.value, "pass_launches": pl.value, "pass_ms": ms.value, "pass_bytes": by.value}
+
+    def pass_breakdown(self):
+        la = (C.c_int64 * 3)()
+        ms, by, fl = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_double * 3)()
+        self._ck(self.lib.dlra_pass_breakdown(self.h, la, ms, by, fl))
+        names = ("fused_KL", "K_only", "L_only")
+        return {nm: {"launches": la[i], "ms": ms[i], "bytes": by[i], "flops": fl[i]} for i, nm in enumerate(names)}
+
+    def event_record(self, slot):
+        self._ck(self.lib.dlra_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        out = C.c_double()
+        self._ck(self.lib.dlra_event_elapsed_ms(self.h, a, b, C.byref(out)))
+        return out.value
