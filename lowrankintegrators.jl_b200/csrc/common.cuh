@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <stdexcept>
+#include <type_traits>
 
 namespace dlra {
 
@@ -39,6 +40,16 @@ struct Ctx {
     int64_t launches = 0;
     int num_sms = 148;
 };
+
+// compile-time loop: f(std::integral_constant<int, I>) for I = B .. E-1 (indices are constant expressions in the
+// front end, so register arrays indexed by them are always promoted — nested `#pragma unroll` is not reliable for that)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // device-side primitives

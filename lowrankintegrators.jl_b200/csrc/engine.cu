@@ -280,11 +280,11 @@ static void end_data_step(dlra_handle h) {
 // shared step pieces
 // ---------------------------------------------------------------------------------------------------
 static void ensure_qr_ws(dlra_handle h, int64_t rows, int C) {
-    const int cb = std::min(C, 32);
+    const int cb = std::min(C, TSQR_MAXC);
     h->tws.ensure(tsqr_ws_size(rows, cb, 8), h->cx.stream);
-    if (C > 32) {
-        h->wtmp.ensure((int64_t)C * 32, h->cx.stream);
-        h->gws.ensure(gemm_tn_ws(h->cx, rows, C, 32), h->cx.stream);
+    if (C > TSQR_MAXC) {
+        h->wtmp.ensure(thin_qr_wtmp(C), h->cx.stream);
+        h->gws.ensure(gemm_tn_ws(h->cx, rows, C, TSQR_MAXC), h->cx.stream);
     }
 }
 // thin QR of an n-side (row sharded) matrix, in place

@@ -2,19 +2,19 @@
 // Replaces `qr!(US)` + `Matrix(QRK.Q)` (LAPACK dgeqrt + dgemqrt) at projector_splitting.jl:137-138,149-151,
 // 174-175,186-188; unconventional.jl:141-142,149-152; rank_adaptive_unconventional.jl:202-205,213-216.
 //
-// Structure (one kernel per tree level, all levels Householder => unconditionally stable, rank-deficient
-// panels included):
-//   tsqr_cta_kernel : each CTA takes BR = NW0*64 rows; every warp factors a 64 x CP panel held in shared
-//                     memory with warp-shuffle reductions (panel_qr), forms its explicit Q in place
-//                     (panel_formq, dorg2r-style), the R factors are stacked and reduced by an in-CTA tree,
-//                     then the explicit Q's are chained top-down so the CTA writes an orthonormal BR x C
-//                     block plus ONE CP x CP R factor.
-//   recursion       : the stacked R factors (nb*CP x CP) are factored by the same kernel until one CTA
-//                     suffices; with row sharding the per-GPU R's are all-gathered (NCCL) and every rank
-//                     redundantly factors the G*CP x CP stack.
+// Every tree node is a Householder factorisation => unconditionally stable, rank-deficient panels included
+// (the DLRA K/L matrices routinely have condition numbers ~1/tol, which rules out Gram/Cholesky-QR variants).
+//   tsqr_reg_kernel : a CTA owns 1024 rows; each of its 8 warps keeps a 128 x CP panel ENTIRELY IN REGISTERS
+//                     (lane l holds rows l, l+32, l+64, l+96), factors it with warp-shuffle reductions
+//                     (one batched butterfly per column gives the norm and all trailing dot products), forms
+//                     its explicit Q in place (dorg2r recurrence), and the 8 stacked R factors are factored the
+//                     same way by warp 0; the explicit Q's are then chained so the CTA writes an orthonormal
+//                     1024 x C block plus ONE CP x CP R factor.
+//   recursion       : the stacked R factors (nb*CP x CP) go through the same kernel until one CTA suffices;
+//                     with row sharding the per-GPU R's are all-gathered (NCCL) and every rank redundantly
+//                     factors the G*CP x CP stack.
 //   apply_blocks    : Q_block <- Q_block * X_block with the CP x CP blocks of the upper level's Q.
-// Columns wider than 32 are handled by block classical Gram-Schmidt with re-orthogonalisation (BCGS2) around
-// 32-column TSQR panels.
+// Columns wider than 16 use block classical Gram-Schmidt with re-orthogonalisation (BCGS2) around 16-column panels.
 #pragma once
 #include "common.cuh"
 #include "comm.cuh"
@@ -22,206 +22,208 @@
 
 namespace dlra {
 
-constexpr int TSQR_PLD = 65;  // panel leading dimension (64 rows + 1 pad): conflict-light for row- and column-parallel access
+constexpr int TSQR_NW = 8;      // warps per CTA
+constexpr int TSQR_RPL0 = 4;    // rows per lane at level 0 (128-row panels)
+constexpr int TSQR_BR = TSQR_NW * 32 * TSQR_RPL0;  // 1024 rows per CTA
+constexpr int TSQR_MAXC = 16;
 
-template <int CP>
-struct TsqrCfg {
-    static constexpr int NW0 = (CP == 32) ? 4 : 8;   // level-0 warps (panels) per CTA
-    static constexpr int BR = NW0 * 64;              // rows per CTA
-    static constexpr int ARITY = 64 / CP;            // R factors stacked per upper-level panel
-    static constexpr int cnt(int level) { int c = NW0; for (int l = 0; l < level; ++l) c = (c * CP + 63) / 64; return c; }
-    static constexpr int levels() { int l = 1, c = NW0; while (c > 1) { c = (c * CP + 63) / 64; ++l; } return l; }
-    static constexpr int offset(int level) { int o = 0; for (int l = 0; l < level; ++l) o += cnt(l); return o; }
-    static constexpr int total() { return offset(levels()); }
-    static constexpr int prows(int level) { return level == 0 ? 64 : ((cnt(level - 1) * CP >= 64) ? 64 : ((cnt(level - 1) * CP + 31) / 32) * 32); }
-    static constexpr size_t smem_bytes() { return (size_t)total() * CP * TSQR_PLD * 8 + (size_t)total() * CP * 8 + (size_t)NW0 * CP * 8; }
-};
-
-// Householder QR of a prows x CP panel P[c*PLD + row] by one warp. R ends in the upper triangle, the
-// Householder vectors (unit diagonal implicit) below it, tau[j] as LAPACK dlarfg (tau = 0 for a zero column).
-template <int CP>
-__device__ void panel_qr(double* P, int prows, double* tau, double* wbuf, int lane) {
-    constexpr int PLD = TSQR_PLD;
+// Householder QR of a (32*RPL) x CP register panel: lane l holds rows l + 32 q.  The loop over columns is a REAL loop
+// (compact code: a fully unrolled factorisation is instruction-fetch bound): the register columns are rotated so the
+// pivot column is always a[.][0]; the finished column j (R above/on the diagonal, the Householder vector below it,
+// unit diagonal implicit) is parked in shared memory `vs` ([CP][VLD], lane <-> row), tau[] as LAPACK dlarfg.
+template <int CP, int RPL>
+__device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, int vld, double* tau_s, int lane) {
+#pragma unroll 1
     for (int j = 0; j < CP; ++j) {
-        double* colj = P + j * PLD;
-        double ss = 0.0;
-        for (int row = lane; row < prows; row += 32)
-            if (row > j) { double x = colj[row]; ss = fma(x, x, ss); }
-        ss = warp_sum(ss);
-        const double alpha = colj[j];
+        double e[CP];
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                const bool act = (q > 0) || (lane > j);
+                s = act ? fma(a[q][0], a[q][c], s) : s;
+            }
+            e[c] = s;
+        }
+#pragma unroll
+        for (int c = 0; c < CP; ++c) e[c] = warp_sum(e[c]);
+        const double alpha = __shfl_sync(0xffffffffu, a[0][0], j);
+        const double ss = e[0];
         double t = 0.0, scale = 0.0, beta = alpha;
         if (ss > 0.0) {
             beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
             t = (beta - alpha) / beta;
             scale = 1.0 / (alpha - beta);
         }
-        __syncwarp();
-        for (int row = lane; row < prows; row += 32)
-            if (row > j) colj[row] *= scale;
-        if (lane == 0) { colj[j] = beta; tau[j] = t; }
-        __syncwarp();
-        if (t != 0.0) {
-            // w_c = tau * v' * P[:,c]   (lane <-> column)
-            for (int c = j + 1 + lane; c < CP; c += 32) {
-                const double* colc = P + c * PLD;
-                double w0 = colc[j], w1 = 0.0, w2 = 0.0, w3 = 0.0;
-                int row = j + 1;
-                for (; row + 3 < prows; row += 4) {
-                    w0 = fma(colj[row], colc[row], w0);
-                    w1 = fma(colj[row + 1], colc[row + 1], w1);
-                    w2 = fma(colj[row + 2], colc[row + 2], w2);
-                    w3 = fma(colj[row + 3], colc[row + 3], w3);
-                }
-                for (; row < prows; ++row) w0 = fma(colj[row], colc[row], w0);
-                wbuf[c] = ((w0 + w1) + (w2 + w3)) * t;
-            }
-            __syncwarp();
-            // P[:,c] -= v * w_c       (lane <-> row)
-            for (int c = j + 1; c < CP; ++c) {
-                const double w = wbuf[c];
-                double* colc = P + c * PLD;
-                for (int row = lane; row < prows; row += 32) {
-                    if (row > j) colc[row] = fma(-w, colj[row], colc[row]);
-                    else if (row == j) colc[row] -= w;
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
-// In-place explicit thin Q (prows x CP) from the Householder vectors left by panel_qr (LAPACK dorg2r).
-// The upper triangle (R) must have been copied out before.
-template <int CP>
-__device__ void panel_formq(double* P, int prows, const double* tau, double* wbuf, int lane) {
-    constexpr int PLD = TSQR_PLD;
-    for (int j = CP - 1; j >= 0; --j) {
-        double* colj = P + j * PLD;
-        const double t = tau[j];
-        // rows < j of columns > j are already zero; row j of columns > j currently holds R -> must read as 0
-        if (t != 0.0 && j + 1 < CP) {
-            for (int c = j + 1 + lane; c < CP; c += 32) {
-                const double* colc = P + c * PLD;
-                double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;  // Q[j][c] == 0 before H_j is applied
-                int row = j + 1;
-                for (; row + 3 < prows; row += 4) {
-                    w0 = fma(colj[row], colc[row], w0);
-                    w1 = fma(colj[row + 1], colc[row + 1], w1);
-                    w2 = fma(colj[row + 2], colc[row + 2], w2);
-                    w3 = fma(colj[row + 3], colc[row + 3], w3);
-                }
-                for (; row < prows; ++row) w0 = fma(colj[row], colc[row], w0);
-                wbuf[c] = ((w0 + w1) + (w2 + w3)) * t;
-            }
-            __syncwarp();
-            for (int c = j + 1; c < CP; ++c) {
-                const double w = wbuf[c];
-                double* colc = P + c * PLD;
-                for (int row = lane; row < prows; row += 32) {
-                    if (row > j) colc[row] = fma(-w, colj[row], colc[row]);
-                    else if (row == j) colc[row] = -w;
-                }
-            }
-        } else {
-            for (int c = j + 1 + lane; c < CP; c += 32) P[c * PLD + j] = 0.0;
-        }
-        __syncwarp();
-        for (int row = lane; row < prows; row += 32) {
-            if (row > j) colj[row] = -t * colj[row];
-            else if (row == j) colj[row] = 1.0 - t;
-            else colj[row] = 0.0;
-        }
-        __syncwarp();
-    }
-}
-
-template <int CP>
-__global__ void __launch_bounds__(TsqrCfg<CP>::NW0 * 32) tsqr_cta_kernel(int64_t rows, int C, const double* __restrict__ A, int64_t lda,
-                                                                       double* __restrict__ Q, int64_t ldq,
-                                                                       double* __restrict__ Rstack, int64_t ldr) {
-    using Cfg = TsqrCfg<CP>;
-    constexpr int PLD = TSQR_PLD;
-    constexpr int NL = Cfg::levels();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double* panels = reinterpret_cast<double*>(smem_raw);
-    double* taus = panels + (size_t)Cfg::total() * CP * PLD;
-    double* wbufs = taus + (size_t)Cfg::total() * CP;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t row0 = (int64_t)blockIdx.x * Cfg::BR;
-    double* wbuf = wbufs + warp * CP;
-
-    // ---- level 0 load (zero padded rows / columns)
-    {
-        double* P = panels + (size_t)warp * CP * PLD;
-        for (int c = 0; c < CP; ++c)
+        if (lane == 0) tau_s[j] = t;
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int row = lane + 32 * q;
-                const int64_t g = row0 + warp * 64 + row;
-                P[c * PLD + row] = (g < rows && c < C) ? A[g + (int64_t)c * lda] : 0.0;
+        for (int q = 0; q < RPL; ++q) {
+            const bool act = (q > 0) || (lane > j);
+            a[q][0] = act ? a[q][0] * scale : a[q][0];
+        }
+        a[0][0] = (lane == j) ? beta : a[0][0];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) vs[j * vld + lane + 32 * q] = a[q][0];
+        // apply H_j to the trailing columns and rotate them one position to the left
+#pragma unroll
+        for (int c = 1; c < CP; ++c) {
+            const double arow = __shfl_sync(0xffffffffu, a[0][c], j);
+            const double w = (arow + e[c] * scale) * t;
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                const bool act = (q > 0) || (lane > j);
+                double x = a[q][c];
+                x = act ? fma(-w, a[q][0], x) : x;
+                if (q == 0) x = (lane == j) ? x - w : x;
+                a[q][c] = x;
             }
+        }
+#pragma unroll
+        for (int c = 1; c < CP; ++c)
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) a[q][c - 1] = a[q][c];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) a[q][CP - 1] = 0.0;
     }
     __syncwarp();
-    // ---- up-sweep
+}
+
+// Explicit thin Q (32*RPL x CP) into registers from the vectors parked by reg_panel_qr (LAPACK dorg2r recurrence, looped
+// with rotating register columns: position c holds Q column j+1+c-1 while column j is being built).
+template <int CP, int RPL>
+__device__ __forceinline__ void reg_panel_formq(double (&a)[RPL][CP], const double* vs, int vld, const double* tau_s, int lane) {
 #pragma unroll
-    for (int lev = 0; lev < NL; ++lev) {
-        const int cnt = Cfg::cnt(lev);
-        if (warp < cnt) {
-            double* P = panels + (size_t)(Cfg::offset(lev) + warp) * CP * PLD;
-            double* tau = taus + (size_t)(Cfg::offset(lev) + warp) * CP;
-            const int prows = Cfg::prows(lev);
-            panel_qr<CP>(P, prows, tau, wbuf, lane);
-            // copy R (upper triangle, zeros below) to the parent panel or to the global stack
-            if (lev + 1 < NL) {
-                double* Pp = panels + (size_t)(Cfg::offset(lev + 1) + warp / Cfg::ARITY) * CP * PLD;
-                const int roff = (warp % Cfg::ARITY) * CP;
-                for (int e = lane; e < CP * CP; e += 32) {
-                    int i = e % CP, c = e / CP;
-                    Pp[c * PLD + roff + i] = (i <= c) ? P[c * PLD + i] : 0.0;
-                }
-            } else {
-                for (int e = lane; e < CP * CP; e += 32) {
-                    int i = e % CP, c = e / CP;
-                    Rstack[(int64_t)blockIdx.x * CP + i + (int64_t)c * ldr] = (i <= c) ? P[c * PLD + i] : 0.0;
-                }
-            }
-            __syncwarp();
-            panel_formq<CP>(P, prows, tau, wbuf, lane);
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) a[q][c] = 0.0;
+#pragma unroll 1
+    for (int j = CP - 1; j >= 0; --j) {
+        const double t = tau_s[j];
+        double v[RPL];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            const bool act = (q > 0) || (lane > j);
+            v[q] = act ? vs[j * vld + lane + 32 * q] : 0.0;
         }
-        __syncthreads();
-    }
-    // ---- down-sweep: Q_panel <- Q_panel * X, X = CP x CP row block of the parent's (already final) panel
+        // rotate right: make room for column j at position 0
 #pragma unroll
-    for (int lev = NL - 2; lev >= 0; --lev) {
-        const int cnt = Cfg::cnt(lev);
-        if (warp < cnt) {
-            double* P = panels + (size_t)(Cfg::offset(lev) + warp) * CP * PLD;
-            const double* X = panels + (size_t)(Cfg::offset(lev + 1) + warp / Cfg::ARITY) * CP * PLD + (warp % Cfg::ARITY) * CP;
-            const int prows = Cfg::prows(lev);
-            for (int row = lane; row < prows; row += 32) {
-                double x[CP];
+        for (int c = CP - 1; c >= 1; --c)
 #pragma unroll
-                for (int k = 0; k < CP; ++k) x[k] = P[k * PLD + row];
-                for (int c = 0; c < CP; ++c) {
-                    double s = 0.0;
+            for (int q = 0; q < RPL; ++q) a[q][c] = a[q][c - 1];
 #pragma unroll
-                    for (int k = 0; k < CP; ++k) s = fma(x[k], X[c * PLD + k], s);
-                    P[c * PLD + row] = s;
-                }
+        for (int c = 1; c < CP; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) s = fma(v[q], a[q][c], s);
+            const double w = warp_sum(s) * t;   // Q[j][c] == 0 before H_j is applied
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                double x = fma(-w, v[q], a[q][c]);
+                if (q == 0) x = (lane == j) ? -w : x;
+                a[q][c] = x;
             }
         }
-        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            double x = -t * v[q];
+            if (q == 0) x = (lane == j) ? 1.0 - t : x;
+            a[q][0] = x;
+        }
     }
-    // ---- store the explicit Q block
+}
+
+template <int CP>
+struct TsqrSmem {
+    static constexpr int SROWS = TSQR_NW * CP;                 // rows of the stacked R panel
+    static constexpr int PROWS = 32 * TSQR_RPL0;               // rows of a level-0 panel
+    static constexpr size_t STACK = (size_t)CP * (SROWS + 1);  // doubles
+    static constexpr size_t PARK = (size_t)TSQR_NW * CP * PROWS;
+    static constexpr size_t BYTES = (2 * STACK + PARK + (size_t)TSQR_NW * CP) * sizeof(double);
+};
+
+// warp 0: factor the NW*CP x CP stack of R factors (in shared memory), write R to global and leave the explicit Q in place.
+template <int CP>
+__device__ __noinline__ void tsqr_level1(double* stack, double* stack2, double* taus, double* Rout, int64_t ldr, int lane) {
+    constexpr int RPL1 = TSQR_NW * CP / 32;
+    constexpr int SLD = TSQR_NW * CP + 1;
+    double b[RPL1][CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+        for (int q = 0; q < RPL1; ++q) b[q][c] = stack[c * SLD + lane + 32 * q];
+    reg_panel_qr<CP, RPL1>(b, stack2, SLD, taus, lane);
+    if (lane < CP) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) Rout[lane + (int64_t)c * ldr] = (lane <= c) ? stack2[c * SLD + lane] : 0.0;
+    }
+    reg_panel_formq<CP, RPL1>(b, stack2, SLD, taus, lane);
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+        for (int q = 0; q < RPL1; ++q) stack[c * SLD + lane + 32 * q] = b[q][c];
+}
+
+template <int CP>
+__global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows, int C, const double* __restrict__ A, int64_t lda,
+                                                                  double* __restrict__ Q, int64_t ldq,
+                                                                  double* __restrict__ Rstack, int64_t ldr) {
+    using SM = TsqrSmem<CP>;
+    constexpr int RPL0 = TSQR_RPL0;
+    constexpr int SLD = SM::SROWS + 1;
+    constexpr int PROWS = SM::PROWS;
+    extern __shared__ __align__(16) double tsm[];
+    double* stack = tsm;                          // [CP][SLD]: stacked R factors, later the explicit level-1 Q
+    double* stack2 = stack + SM::STACK;           // [CP][SLD]: Householder vectors of the level-1 factorisation
+    double* park = stack2 + SM::STACK;            // [NW][CP][PROWS]: per warp: Householder vectors, then the explicit level-0 Q
+    double* taus = park + SM::PARK;               // [NW][CP]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row0 = (int64_t)blockIdx.x * TSQR_BR + warp * PROWS;
+    double* mypark = park + (size_t)warp * CP * PROWS;
     {
-        const double* P = panels + (size_t)warp * CP * PLD;
-        for (int c = 0; c < C; ++c)
+        double a[RPL0][CP];
+        bool ok[RPL0];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int row = lane + 32 * q;
-                const int64_t g = row0 + warp * 64 + row;
-                if (g < rows) Q[g + (int64_t)c * ldq] = P[c * PLD + row];
-            }
+        for (int q = 0; q < RPL0; ++q) ok[q] = (row0 + lane + 32 * q) < rows;
+        const double* col = A + row0 + lane;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+#pragma unroll
+            for (int q = 0; q < RPL0; ++q) a[q][c] = (ok[q] && c < C) ? col[32 * q] : 0.0;
+            col += lda;
+        }
+        reg_panel_qr<CP, RPL0>(a, mypark, PROWS, taus + warp * CP, lane);
+        // R_w -> rows [CP*warp, CP*warp + CP) of the stack (zeros below the diagonal)
+        if (lane < CP) {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) stack[c * SLD + CP * warp + lane] = (lane <= c) ? mypark[c * PROWS + lane] : 0.0;
+        }
+        reg_panel_formq<CP, RPL0>(a, mypark, PROWS, taus + warp * CP, lane);
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CP; ++c)
+#pragma unroll
+            for (int q = 0; q < RPL0; ++q) mypark[c * PROWS + lane + 32 * q] = a[q][c];
+    }
+    __syncthreads();
+    if (warp == 0) tsqr_level1<CP>(stack, stack2, taus, Rstack + (int64_t)blockIdx.x * CP, ldr, lane);
+    __syncthreads();
+    // Q_w <- Q_w * X_w,  X_w = rows [CP*warp, +CP) of the explicit level-1 Q
+#pragma unroll 1
+    for (int q = 0; q < RPL0; ++q) {
+        double x[CP];
+#pragma unroll
+        for (int k = 0; k < CP; ++k) x[k] = mypark[k * PROWS + lane + 32 * q];
+        const bool okq = (row0 + lane + 32 * q) < rows;
+        double* qcol = Q + row0 + lane + 32 * q;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < CP; ++k) s = fma(x[k], stack[c * SLD + CP * warp + k], s);
+            if (okq && c < C) *qcol = s;
+            qcol += ldq;
+        }
     }
 }
 
@@ -242,29 +244,23 @@ __global__ void __launch_bounds__(128) apply_blocks_kernel(int64_t rows, int C, 
     double x[CP];
 #pragma unroll
     for (int k = 0; k < CP; ++k) x[k] = (k < C) ? Q[i + (int64_t)k * ldq] : 0.0;
-    for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
         double s = 0.0;
 #pragma unroll
         for (int k = 0; k < CP; ++k) s = fma(x[k], Xs[k][c], s);
-        Q[i + (int64_t)c * ldq] = s;
+        if (c < C) Q[i + (int64_t)c * ldq] = s;
     }
 }
 
-struct TsqrWorkspace {
-    double* buf = nullptr;  // device doubles
-    int64_t size = 0;
-};
+inline int tsqr_cp(int C) { return C <= 8 ? 8 : 16; }
 
-inline int tsqr_cp(int C) { return C <= 8 ? 8 : (C <= 16 ? 16 : 32); }
-inline int64_t tsqr_br(int CP) { return CP == 32 ? TsqrCfg<32>::BR : TsqrCfg<16>::BR; }
-
-// doubles of scratch for a rows x C (C <= 32) TSQR incl. recursion and the optional NCCL gather stage
+// doubles of scratch for a rows x C (C <= 16) TSQR incl. recursion and the optional NCCL gather stage
 inline int64_t tsqr_ws_size(int64_t rows, int C, int nranks) {
     const int CP = tsqr_cp(C);
-    const int64_t BR = tsqr_br(CP);
     int64_t total = 0, r = rows;
     while (true) {
-        int64_t nb = cdiv(r, BR);
+        int64_t nb = cdiv(r, TSQR_BR);
         total += 2 * nb * CP * CP;  // Rstack + Qtop of this level
         if (nb == 1) break;
         r = nb * CP;
@@ -273,68 +269,60 @@ inline int64_t tsqr_ws_size(int64_t rows, int C, int nranks) {
     return total + 1024;
 }
 
-template <int CP>
-inline void tsqr_launch(Ctx& cx, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* Rstack, int64_t ldr) {
-    using Cfg = TsqrCfg<CP>;
+inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* Rstack, int64_t ldr) {
+    const unsigned nb = (unsigned)cdiv(rows, TSQR_BR);
     static bool attr_set = false;
     if (!attr_set) {
-        DLRA_CUDA(cudaFuncSetAttribute(tsqr_cta_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::smem_bytes()));
+        DLRA_CUDA(cudaFuncSetAttribute(tsqr_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<8>::BYTES));
+        DLRA_CUDA(cudaFuncSetAttribute(tsqr_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<16>::BYTES));
         attr_set = true;
     }
-    const int64_t nb = cdiv(rows, Cfg::BR);
-    tsqr_cta_kernel<CP><<<(unsigned)nb, Cfg::NW0 * 32, Cfg::smem_bytes(), cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr);
+    if (CP == 8) tsqr_reg_kernel<8><<<nb, TSQR_NW * 32, TsqrSmem<8>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr);
+    else tsqr_reg_kernel<16><<<nb, TSQR_NW * 32, TsqrSmem<16>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr);
     cx.launches++;
     DLRA_CUDA(cudaGetLastError());
-}
-
-inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* Rstack, int64_t ldr) {
-    if (CP == 8) tsqr_launch<8>(cx, rows, C, A, lda, Q, ldq, Rstack, ldr);
-    else if (CP == 16) tsqr_launch<16>(cx, rows, C, A, lda, Q, ldq, Rstack, ldr);
-    else tsqr_launch<32>(cx, rows, C, A, lda, Q, ldq, Rstack, ldr);
 }
 
 inline void apply_blocks(Ctx& cx, int CP, int64_t rows, int C, double* Q, int64_t ldq, int64_t block_rows, const double* X, int64_t ldx, int64_t xstride) {
     unsigned grid = (unsigned)cdiv(rows, 128);
     if (CP == 8) apply_blocks_kernel<8><<<grid, 128, 0, cx.stream>>>(rows, C, Q, ldq, block_rows, X, ldx, xstride);
-    else if (CP == 16) apply_blocks_kernel<16><<<grid, 128, 0, cx.stream>>>(rows, C, Q, ldq, block_rows, X, ldx, xstride);
-    else apply_blocks_kernel<32><<<grid, 128, 0, cx.stream>>>(rows, C, Q, ldq, block_rows, X, ldx, xstride);
+    else apply_blocks_kernel<16><<<grid, 128, 0, cx.stream>>>(rows, C, Q, ldq, block_rows, X, ldx, xstride);
     cx.launches++;
     DLRA_CUDA(cudaGetLastError());
 }
 
-// Local (single GPU) TSQR of A (rows x C, C <= 32): Q (rows x C, may alias A) and Rp = CP x CP padded R (ld = CP).
-// ws must hold tsqr_ws_size doubles.  Returns a pointer (inside ws) to the CP x CP R factor.
+// Local (single GPU) TSQR of A (rows x C, C <= 16): Q (rows x C, may alias A).  Returns a pointer (inside ws) to the
+// CP x CP padded R factor (ld = CP).  ws must hold tsqr_ws_size doubles.
 inline double* tsqr_local(Ctx& cx, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* ws) {
     const int CP = tsqr_cp(C);
-    const int64_t BR = tsqr_br(CP);
-    const int64_t nb = cdiv(rows, BR);
+    const int64_t nb = cdiv(rows, TSQR_BR);
     double* Rstack = ws;                    // (nb*CP) x CP, ld = nb*CP
     double* Qtop = ws + nb * CP * CP;       // same shape
     double* rest = Qtop + nb * CP * CP;
     tsqr_level(cx, CP, rows, C, A, lda, Q, ldq, Rstack, nb * CP);
     if (nb == 1) return Rstack;
     double* Rtop = tsqr_local(cx, nb * CP, CP, Rstack, nb * CP, Qtop, nb * CP, rest);
-    apply_blocks(cx, CP, rows, C, Q, ldq, BR, Qtop, nb * CP, CP);
+    apply_blocks(cx, CP, rows, C, Q, ldq, TSQR_BR, Qtop, nb * CP, CP);
     return Rtop;
 }
 
 // Distributed TSQR: rows are this rank's shard.  R (C x C, ldr) optional output (replicated on all ranks).
 inline void tsqr(Ctx& cx, Comm& comm, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* R, int64_t ldr,
                  double* ws) {
-    DLRA_REQUIRE(C >= 1 && C <= 32, "tsqr panel width must be 1..32");
+    DLRA_REQUIRE(C >= 1 && C <= TSQR_MAXC, "tsqr panel width must be 1..16");
     const int CP = tsqr_cp(C);
     double* tail = ws + tsqr_ws_size(rows, C, comm.nranks) - 1024 - (int64_t)(comm.nranks + 1) * CP * CP * 4;
     double* Rloc = tsqr_local(cx, rows, C, A, lda, Q, ldq, ws);
     const double* Rfin = Rloc;
     if (comm.nranks > 1) {
         const int G = comm.nranks;
-        double* gathered = tail;                       // G blocks of CP x CP (each ld = CP)
+        double* gathered = tail;                                // G blocks of CP x CP (each ld = CP)
         double* stacked = gathered + (int64_t)G * CP * CP;      // (G*CP) x CP, ld = G*CP
         double* Qg = stacked + (int64_t)G * CP * CP;            // (G*CP) x CP
-        double* ws2 = Qg + (int64_t)G * CP * CP;                // CP*CP*? small recursion scratch (G*CP <= BR assumed)
+        double* ws2 = Qg + (int64_t)G * CP * CP;
         comm.allgather(Rloc, gathered, (int64_t)CP * CP, cx.stream);
         for (int g = 0; g < G; ++g) copy_mat(cx, CP, CP, gathered + (int64_t)g * CP * CP, CP, false, stacked + (int64_t)g * CP, (int64_t)G * CP);
-        DLRA_REQUIRE((int64_t)G * CP <= tsqr_br(CP), "too many ranks for the single-CTA R reduction");
+        DLRA_REQUIRE((int64_t)G * CP <= TSQR_BR, "too many ranks for the single-CTA R reduction");
         double* Rg = tsqr_local(cx, (int64_t)G * CP, CP, stacked, (int64_t)G * CP, Qg, (int64_t)G * CP, ws2);
         apply_blocks(cx, CP, rows, C, Q, ldq, (int64_t)1 << 62, Qg + (int64_t)comm.rank * CP, (int64_t)G * CP, 0);
         Rfin = Rg;
@@ -342,28 +330,49 @@ inline void tsqr(Ctx& cx, Comm& comm, int64_t rows, int C, const double* A, int6
     if (R) copy_mat(cx, C, C, Rfin, CP, false, R, ldr);
 }
 
-// Wide thin QR (any C): BCGS2 around <=32-column TSQR panels.  A is overwritten; Q may alias A.
-// R (C x C, ldr) optional.  gws: gemm_tn scratch, Wtmp: C x 32 scratch (device), tws: tsqr scratch.
+// Wide thin QR (any C): block classical Gram-Schmidt with re-orthogonalisation around <=16-column TSQR panels.
+// Per block: project, TSQR, project again, TSQR again (Barlow-Smoktunowicz BCGS2) — the intermediate factorisation makes
+// the second projection act on a perfectly conditioned block, so ||I - Q'Q|| stays O(eps) even when the block is almost
+// contained in the span of the previous ones (the rank-adaptive [K U0] basis always is).
+// A is overwritten; Q may alias A.  R (C x C, ldr) optional.  gws: gemm_tn scratch, Wtmp: thin_qr_wtmp(C) doubles, tws: tsqr scratch.
+inline int64_t thin_qr_wtmp(int C) { return (int64_t)2 * C * TSQR_MAXC + 4 * TSQR_MAXC * TSQR_MAXC; }
+
 inline void thin_qr(Ctx& cx, Comm& comm, int64_t rows, int C, double* A, int64_t lda, double* Q, int64_t ldq, double* R, int64_t ldr,
                     double* tws, double* gws, double* Wtmp) {
-    if (C <= 32) {
+    if (C <= TSQR_MAXC) {
         tsqr(cx, comm, rows, C, A, lda, Q, ldq, R, ldr, tws);
         return;
     }
+    double* W1 = Wtmp;
+    double* W2 = W1 + (int64_t)C * TSQR_MAXC;
+    double* R1 = W2 + (int64_t)C * TSQR_MAXC;
+    double* R2 = R1 + TSQR_MAXC * TSQR_MAXC;
+    constexpr int LR = TSQR_MAXC;
     if (R) fill_mat(cx, C, C, R, ldr, 0.0, 0.0);
-    for (int c0 = 0; c0 < C; c0 += 32) {
-        const int cb = std::min(32, C - c0);
+    for (int c0 = 0; c0 < C; c0 += TSQR_MAXC) {
+        const int cb = std::min(TSQR_MAXC, C - c0);
         double* Ap = A + (int64_t)c0 * lda;
-        if (c0 > 0) {
-            for (int pass = 0; pass < 2; ++pass) {
-                // W = Q[:, :c0]' * Ap  (c0 x cb), all-reduced over row shards
-                gemm_tn(cx, rows, c0, cb, Q, ldq, nullptr, 0, Ap, lda, Wtmp, c0, 1.0, 0.0, gws);
-                comm.allreduce_sum(Wtmp, (int64_t)c0 * cb, cx.stream);
-                gemm_nn(cx, rows, c0, cb, Q, ldq, nullptr, 0, Wtmp, c0, false, Ap, lda, -1.0, 1.0);
-                if (R) copy_mat(cx, c0, cb, Wtmp, c0, false, R + (int64_t)c0 * ldr, ldr, 1.0, pass == 0 ? 0.0 : 1.0);
-            }
+        double* Qp = Q + (int64_t)c0 * ldq;
+        if (c0 == 0) {
+            tsqr(cx, comm, rows, cb, Ap, lda, Qp, ldq, R, ldr, tws);
+            continue;
         }
-        tsqr(cx, comm, rows, cb, Ap, lda, Q + (int64_t)c0 * ldq, ldq, R ? R + c0 + (int64_t)c0 * ldr : nullptr, ldr, tws);
+        // first pass: W1 = Qprev' * Ap ; Ap -= Qprev * W1 ; Ap = Qhat * R1
+        gemm_tn(cx, rows, c0, cb, Q, ldq, nullptr, 0, Ap, lda, W1, c0, 1.0, 0.0, gws);
+        comm.allreduce_sum(W1, (int64_t)c0 * cb, cx.stream);
+        gemm_nn(cx, rows, c0, cb, Q, ldq, nullptr, 0, W1, c0, false, Ap, lda, -1.0, 1.0);
+        tsqr(cx, comm, rows, cb, Ap, lda, Qp, ldq, R1, LR, tws);
+        // second pass on the orthonormal block: W2 = Qprev' * Qhat ; Qhat -= Qprev * W2 ; Qhat = Qp * R2
+        gemm_tn(cx, rows, c0, cb, Q, ldq, nullptr, 0, Qp, ldq, W2, c0, 1.0, 0.0, gws);
+        comm.allreduce_sum(W2, (int64_t)c0 * cb, cx.stream);
+        gemm_nn(cx, rows, c0, cb, Q, ldq, nullptr, 0, W2, c0, false, Qp, ldq, -1.0, 1.0);
+        tsqr(cx, comm, rows, cb, Qp, ldq, Qp, ldq, R ? R2 : nullptr, LR, tws);
+        if (R) {
+            // A_p = Qprev*(W1 + W2*R1) + Qp*(R2*R1)
+            small_gemm(cx, c0, cb, cb, W2, c0, false, R1, LR, false, W1, c0, 1.0, 1.0);
+            copy_mat(cx, c0, cb, W1, c0, false, R + (int64_t)c0 * ldr, ldr);
+            small_gemm(cx, cb, cb, cb, R2, LR, false, R1, LR, false, R + c0 + (int64_t)c0 * ldr, (int)ldr, 1.0, 0.0);
+        }
     }
 }
 
