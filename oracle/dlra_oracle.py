@@ -565,6 +565,9 @@ def step(integ: DLRIntegrator, alg=None, dt=None):
         if adjusted:
             integ.u = u_new
             c.r = u_new.rank  # alg_recache (rank_adaptive_unconventional.jl:133-169): buffers re-sized for r_new
+            if not c.is_data:  # ... and the ODE integrators are re-`init`ed (:150-164): fresh controller state
+                for st in (c.K_alg, c.L_alg, c.S_alg):
+                    st.dt_next, st.qold = None, 1e-4
     elif isinstance(alg, GreedyIntegrator):
         greedy_step(u, c, t, dt)
     else:
