@@ -221,8 +221,9 @@ def _fetch(y, t, dt):
 
 def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False) -> DLRIntegrator:
     """init(prob, alg, dt): projector_splitting.jl:107-115, unconventional.jl:109-119,
-    rank_adaptive_unconventional.jl:94-104, greedy_integrator.jl:49-59.  `comm` = (nranks, rank, unique_id) row-shards
-    the problem: every rank passes ITS row block of u0.U and of the snapshots."""
+    rank_adaptive_unconventional.jl:94-104, greedy_integrator.jl:49-59.  `comm` = "torch" (use the initialised torch.distributed group to distribute
+    a fresh ncclUniqueId) or (nranks, rank, unique_id) row-shards the problem: every rank passes ITS row block of u0.U
+    and of the snapshots.  A unique id can initialise ONE communicator only."""
     t0, tf = prob.tspan
     assert tf > t0, "Integration in reverse time direction is not supported"
     u0 = prob.u0
@@ -234,6 +235,9 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
         rmax = int(min(alg.rmax, 128, m // 2 if m >= 2 else 1))
         rmax = max(rmax, r0)
     eng = Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic)
+    if comm == "torch":  # one fresh ncclUniqueId per engine, handed out through torch.distributed
+        from .distributed import comm_from_torch
+        comm = comm_from_torch()
     if comm is not None and comm[0] > 1:
         eng.comm_init(*comm)
     eng.set_factors(u0.U, u0.S, u0.V)  # deepcopy(prob.u0)
