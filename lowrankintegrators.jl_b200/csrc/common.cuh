@@ -39,6 +39,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     int64_t launches = 0;
     int num_sms = 148;
+    unsigned int* counters = nullptr;   // zero-initialised device counters for last-block-done reductions (self-resetting)
 };
 
 // compile-time loop: f(std::integral_constant<int, I>) for I = B .. E-1 (indices are constant expressions in the

@@ -66,6 +66,8 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         e->S = sb; sb += W * W; e->M = sb; sb += W * W; e->N = sb; sb += W * W; e->Sh = sb; sb += W * W;
         e->T1 = sb; sb += W * W; e->T2 = sb; sb += W * W; e->Rm = sb; sb += W * W; e->Pm = sb; sb += W * W;
         e->Qm = sb; sb += W * W; e->sig = sb; sb += W; e->scal_dev = sb + W;
+        DLRA_CUDA(cudaMalloc(&e->cx.counters, 256 * sizeof(unsigned int)));
+        DLRA_CUDA(cudaMemsetAsync(e->cx.counters, 0, 256 * sizeof(unsigned int), e->cx.stream));
         DLRA_CUDA(cudaMalloc(&e->r_new_dev, sizeof(int)));
         DLRA_CUDA(cudaHostAlloc(&e->r_new_host, sizeof(int), cudaHostAllocDefault));
         *e->r_new_host = r0;
@@ -92,7 +94,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     cudaStreamSynchronize(h->copy_stream);
     h->comm.destroy();
     cudaFree(h->U); cudaFree(h->UB); cudaFree(h->V); cudaFree(h->VB); cudaFree(h->small_block);
-    cudaFree(h->r_new_dev); cudaFreeHost(h->r_new_host);
+    cudaFree(h->r_new_dev); cudaFreeHost(h->r_new_host); cudaFree(h->cx.counters);
     for (int i = 0; i < 3; ++i) { if (h->own[i]) cudaFree(h->own[i]); cudaEventDestroy(h->own_free[i]); cudaEventDestroy(h->own_ready[i]); }
     h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release();
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }

@@ -136,6 +136,78 @@ inline void reduce_parts(Ctx& cx, int p, int q, int nchunks, const double* part,
     DLRA_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gram-type product for small outputs on the fp64 tensor pipe, ONE launch:
+//   C[16-block (y), 16-block (z)] = beta*C + alpha * A[:, y-block]' * B[:, z-block]      (rows = long reduction)
+// Each warp strides over 4-row slabs (DMMA k = 4; fragments are 32-byte runs of the column-major operands), the 8 warps'
+// tiles are summed in shared memory, every CTA stores one partial and the LAST CTA to finish (ticket counter) adds the
+// partials in fixed order — deterministic without a second launch.
+// ------------------------------------------------------------------------------------------------
+constexpr int GRAM_ROWS_PER_CTA = 1024;
+__global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
+                                                        const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
+                                                        double alpha, double beta, double* __restrict__ part, unsigned int* __restrict__ counters) {
+    __shared__ double red[8][256];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k = lane & 3;
+    const int a0 = blockIdx.y * 16, b0 = blockIdx.z * 16;
+    const int64_t r0 = (int64_t)blockIdx.x * GRAM_ROWS_PER_CTA, r1 = min(n, r0 + GRAM_ROWS_PER_CTA);
+    double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+    const bool a_ok[2] = {a0 + g < p, a0 + 8 + g < p};
+    const bool b_ok[2] = {b0 + g < q, b0 + 8 + g < q};
+    const double* Ap[2] = {A + (int64_t)(a0 + g) * lda, A + (int64_t)(a0 + 8 + g) * lda};
+    const double* Bp[2] = {B + (int64_t)(b0 + g) * ldb, B + (int64_t)(b0 + 8 + g) * ldb};
+    for (int64_t row = r0 + 4 * warp; row < r1; row += 32) {
+        const int64_t i = row + k;
+        const bool ok = i < r1;
+        double af[2], bf[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            af[h] = (ok && a_ok[h]) ? Ap[h][i] : 0.0;
+            bf[h] = (ok && b_ok[h]) ? Bp[h][i] : 0.0;
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+    }
+    // C fragment: rows (mb*8 + g), cols (nb*8 + 2k + e)
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) red[warp][(mb * 8 + g) + 16 * (nb * 8 + 2 * k + e)] = acc[mb][nb][e];
+    __syncthreads();
+    const int nblk = gridDim.x;
+    const int slot = blockIdx.y * gridDim.z + blockIdx.z;
+    double* mypart = part + ((int64_t)slot * nblk + blockIdx.x) * 256;
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        mypart[threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&counters[slot], 1u);
+        is_last = (ticket == (unsigned int)nblk - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s = 0.0;
+    const double* base = part + (int64_t)slot * nblk * 256 + threadIdx.x;
+    for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * 256);
+    const int i = threadIdx.x % 16, j = threadIdx.x / 16;
+    if (a0 + i < p && b0 + j < q) {
+        double* dst = C + (a0 + i) + (int64_t)(b0 + j) * ldc;
+        *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
+    }
+    if (threadIdx.x == 0) counters[slot] = 0;   // self-reset for the next launch on this stream
+}
+
 // workspace (doubles) needed by gemm_tn for the partial sums
 inline int64_t gemm_tn_chunks(const Ctx& cx, int64_t n, int p, int q) {
     int64_t blocks = cdiv(p, 32) * cdiv(q, 32);
@@ -144,12 +216,24 @@ inline int64_t gemm_tn_chunks(const Ctx& cx, int64_t n, int p, int q) {
     if (chunk_rows < 256) chunk_rows = 256;
     return cdiv(n, chunk_rows);
 }
-inline int64_t gemm_tn_ws(const Ctx& cx, int64_t n, int p, int q) { return gemm_tn_chunks(cx, n, p, q) * p * q; }
+inline bool gram_fast_ok(const Ctx& cx, int p, int q) { return cx.counters != nullptr && cdiv(p, 16) * cdiv(q, 16) <= 256; }
+inline int64_t gemm_tn_ws(const Ctx& cx, int64_t n, int p, int q) {
+    const int64_t generic = gemm_tn_chunks(cx, n, p, q) * p * q;
+    const int64_t fast = cdiv(p, 16) * cdiv(q, 16) * cdiv(n, GRAM_ROWS_PER_CTA) * 256;
+    return std::max(generic, fast);
+}
 
 // C[p x q] = beta*C + alpha * (A - Aprev)' * B
 inline void gemm_tn(Ctx& cx, int64_t n, int p, int q, const double* A, int64_t lda, const double* Aprev, int64_t ldap,
                     const double* B, int64_t ldb, double* C, int64_t ldc, double alpha, double beta, double* ws) {
     if (p <= 0 || q <= 0) return;
+    if (!Aprev && gram_fast_ok(cx, p, q)) {
+        dim3 grid((unsigned)cdiv(n, GRAM_ROWS_PER_CTA), (unsigned)cdiv(p, 16), (unsigned)cdiv(q, 16));
+        gram_dmma_kernel<<<grid, 256, 0, cx.stream>>>(n, p, q, A, lda, B, ldb, C, ldc, alpha, beta, ws, cx.counters);
+        cx.launches++;
+        DLRA_CUDA(cudaGetLastError());
+        return;
+    }
     int64_t nch = gemm_tn_chunks(cx, n, p, q);
     int64_t chunk_rows = round_up(cdiv(n, nch), 64);
     nch = cdiv(n, chunk_rows);
