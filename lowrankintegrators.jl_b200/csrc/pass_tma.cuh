@@ -26,7 +26,8 @@ constexpr int PT_SI = 64;        // rows per stage
 constexpr int PT_TJ = 32;        // columns per stage
 constexpr int PT_NSUB_MAX = 7;   // stages (row sub-tiles) per panel held in K accumulators
 constexpr int PT_CONSUMERS = 8;  // consumer warps
-constexpr int PT_THREADS = (PT_CONSUMERS + 1) * 32;
+constexpr int PT_THREADS = (PT_CONSUMERS + 2) * 32;   // + TMA producer warp + L-reducer warp
+constexpr int PT_LRED_LD = PT_TJ + 2;                 // padded column stride of the L reduction buffer (conflict-free)
 constexpr int PT_TBYTES = PT_SI * PT_TJ * 8;  // 16 KB
 constexpr int PT_BOXBYTES = 16 * PT_TJ * 8;   // 4 KB: one 16-row box
 
@@ -47,7 +48,7 @@ struct PassSmem {
     static constexpr int STAGE_BYTES = ((PT_TBYTES * (DIFF ? 2 : 1) + VBYTES + 1023) / 1024) * 1024;
     static constexpr int UBOX_BYTES = 16 * RT * 8;
     static constexpr int UPANEL_BYTES = DO_L ? PT_NSUB_MAX * 4 * UBOX_BYTES : 0;
-    static constexpr int LRED_BYTES = DO_L ? PT_CONSUMERS * PT_TJ * RT * 8 : 0;
+    static constexpr int LRED_BYTES = DO_L ? ((PT_CONSUMERS * PT_LRED_LD * RT * 8 + 1023) / 1024) * 1024 : 0;
     static constexpr int BUDGET = 225 * 1024;
     static constexpr int NST_RAW = (BUDGET - UPANEL_BYTES - LRED_BYTES - 1024) / STAGE_BYTES;
     static constexpr int NST = NST_RAW > 8 ? 8 : NST_RAW;
@@ -61,6 +62,7 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     using SM = PassSmem<RT, DO_K, DO_L, DIFF>;
     constexpr int NST = SM::NST;
     constexpr int NB = RT / 8;
+    constexpr int LD = PT_LRED_LD;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned carve-up (SWIZZLE_128B boxes need it)
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -71,11 +73,15 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint64_t* full = bars;
     uint64_t* empty = bars + NST;
     uint64_t* panel_done = bars + 2 * NST;
+    uint64_t* lfull = bars + 2 * NST + 1;
+    uint64_t* lfree = bars + 2 * NST + 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], PT_CONSUMERS); }
         mbar_init(panel_done, PT_CONSUMERS);
+        mbar_init(lfull, PT_CONSUMERS);
+        mbar_init(lfree, 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -109,7 +115,11 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                             tma_load_2d(sb + b * PT_BOXBYTES, &mapA, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
                             if (DIFF) tma_load_2d(sb + PT_TBYTES + b * PT_BOXBYTES, &mapP, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
                         }
-                        if (DO_K && s == 0) tma_load_2d(sb + PT_TBYTES * (DIFF ? 2 : 1), &mapV, jt * PT_TJ, 0, &full[stage], pol_keep);
+                        if (DO_K && s == 0) {
+#pragma unroll
+                            for (int b = 0; b < 2; ++b)
+                                tma_load_2d(sb + PT_TBYTES * (DIFF ? 2 : 1) + b * (16 * RT * 8), &mapV, jt * PT_TJ + 16 * b, 0, &full[stage], pol_keep);
+                        }
                         if (DO_L && jt == 0) {
 #pragma unroll
                             for (int b = 0; b < 4; ++b)
@@ -117,6 +127,30 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         }
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
+                }
+            }
+        }
+        return;
+    }
+    if (warp == PT_CONSUMERS + 1) {
+        // ------------------------------ L reducer: sums the 8 consumer warps' partial L tiles off the critical path ---
+        if (DO_L) {
+            uint32_t ph = 0;
+            for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
+                double* lp = prm.Lpart + (size_t)panel * prm.ldlp * RT;
+                for (int jt = 0; jt < prm.ntj; ++jt) {
+                    mbar_wait(lfull, ph);
+#pragma unroll 4
+                    for (int i = 0; i < RT; ++i) {   // element (c = i, j = lane)
+                        double sum = 0.0;
+#pragma unroll
+                        for (int w = 0; w < PT_CONSUMERS; ++w) sum += lred[(size_t)w * LD * RT + i * LD + lane];
+                        const int64_t col = (int64_t)jt * PT_TJ + lane;
+                        if (col < prm.m) lp[col + (int64_t)i * prm.ldlp] = sum;
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(lfree);
+                    ph ^= 1;
                 }
             }
         }
@@ -137,10 +171,14 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         const int lrow = (k & 1) + ((k >> 1) & 1) * 8 + 2 * kk + 4 * wblk;
         offL[kk] = g * 128 + (((lrow >> 1) ^ g) << 4) + (lrow & 1) * 8;
     }
+    // V fragment of the K-use: Vf[4*ks + k][8*nb + g] from two swizzled 16-row boxes ([c][16 rows], 128 B per column)
+    uint32_t offV[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) offV[q] = g * 128 + ((((2 * q) + (k >> 1)) ^ g) << 4) + (k & 1) * 8;
     // rows of this thread's C fragments inside a stage
     const int crow = wbox * 16 + prow;
 
-    int stage = 0; uint32_t phase = 0;
+    int stage = 0; uint32_t phase = 0; uint32_t lfree_ph = 1;   // first wait on a fresh barrier passes
     for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
         const int64_t row0 = (int64_t)panel * nsub * PT_SI;
         double kacc[PT_NSUB_MAX][NB][2];
@@ -163,36 +201,22 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             for (int s = 0; s < PT_NSUB_MAX; ++s) {
                 if (s < nsub) {
                     mbar_wait(&full[stage], phase);
-                    unsigned char* sb = stages + (size_t)stage * SM::STAGE_BYTES;
-                    unsigned char* tb = sb + wbox * PT_BOXBYTES;
+                    const unsigned char* sb = stages + (size_t)stage * SM::STAGE_BYTES;
+                    const unsigned char* tb = sb + wbox * PT_BOXBYTES;
                     if (DO_K && s == 0) {
-                        // B fragments of the K-use for this column tile: Vf[4*ks + k][8*nb + g], V tile is dense [c][32]
-                        const double* vt = reinterpret_cast<const double*>(sb + PT_TBYTES * (DIFF ? 2 : 1));
+                        const unsigned char* vt = sb + PT_TBYTES * (DIFF ? 2 : 1);
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks)
 #pragma unroll
-                            for (int nb = 0; nb < NB; ++nb) vf[ks][nb] = vt[(8 * nb + g) * PT_TJ + 4 * ks + k];
-                    }
-                    if (DIFF) {
-                        // ΔA = A − Aprev on this warp's own 8 rows x 32 cols (rows come in adjacent pairs = 16-byte chunks)
-                        unsigned char* pb = tb + PT_TBYTES;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int ch = lane + 32 * i;           // 128 chunks: column = ch >> 2, pair index = ch & 3
-                            const int col = ch >> 2, pr = ch & 3;   // pair rows: {0,1},{8,9},{2,3},{10,11} (+4*wblk)
-                            const int rowp = ((pr & 1) * 8 + (pr >> 1) * 2 + 4 * wblk) >> 1;   // row >> 1
-                            const uint32_t off = col * 128 + ((rowp ^ (col & 7)) << 4);
-                            double2 a = *reinterpret_cast<double2*>(tb + off);
-                            const double2 p = *reinterpret_cast<const double2*>(pb + off);
-                            a.x -= p.x; a.y -= p.y;
-                            *reinterpret_cast<double2*>(tb + off) = a;
-                        }
-                        __syncwarp();
+                            for (int nb = 0; nb < NB; ++nb)
+                                vf[ks][nb] = *reinterpret_cast<const double*>(vt + (ks >> 2) * (16 * RT * 8) + nb * 1024 + offV[ks & 3]);
                     }
                     if (DO_K) {
 #pragma unroll
                         for (int ks = 0; ks < 8; ++ks) {
-                            const double a = *reinterpret_cast<const double*>(tb + ((ks & 1) ? offKo : offKe) + ks * 512);
+                            const uint32_t off = ((ks & 1) ? offKo : offKe) + ks * 512;
+                            double a = *reinterpret_cast<const double*>(tb + off);
+                            if (DIFF) a -= *reinterpret_cast<const double*>(tb + PT_TBYTES + off);   // ΔA = A − Aprev
 #pragma unroll
                             for (int nb = 0; nb < NB; ++nb) dmma884(kacc[s][nb][0], kacc[s][nb][1], a, vf[ks][nb]);
                         }
@@ -206,41 +230,33 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                             for (int nb = 0; nb < NB; ++nb) uf[nb] = *reinterpret_cast<const double*>(ub + offL[kk] + nb * 1024);
 #pragma unroll
                             for (int cb = 0; cb < 4; ++cb) {
-                                const double a = *reinterpret_cast<const double*>(tb + offL[kk] + cb * 1024);
+                                const uint32_t off = offL[kk] + cb * 1024;
+                                double a = *reinterpret_cast<const double*>(tb + off);
+                                if (DIFF) a -= *reinterpret_cast<const double*>(tb + PT_TBYTES + off);
 #pragma unroll
                                 for (int nb = 0; nb < NB; ++nb) dmma884(lacc[cb][nb][0], lacc[cb][nb][1], a, uf[nb]);
                             }
                         }
                     }
-                    if (DIFF) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[stage]);
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
             if (DO_L) {
-                // in-CTA reduction of the 8 warps' partial L tiles, then one coalesced store of the panel partial
-                double* mine = lred + (size_t)warp * PT_TJ * RT;
+                // hand this warp's partial L tile (32 cols x RT) to the reducer warp
+                mbar_wait(lfree, lfree_ph);
+                lfree_ph ^= 1;
+                double* mine = lred + (size_t)warp * LD * RT;
 #pragma unroll
                 for (int cb = 0; cb < 4; ++cb)
 #pragma unroll
                     for (int nb = 0; nb < NB; ++nb) {
-                        mine[(8 * nb + 2 * k) * PT_TJ + 8 * cb + g] = lacc[cb][nb][0];
-                        mine[(8 * nb + 2 * k + 1) * PT_TJ + 8 * cb + g] = lacc[cb][nb][1];
+                        mine[(8 * nb + 2 * k) * LD + 8 * cb + g] = lacc[cb][nb][0];
+                        mine[(8 * nb + 2 * k + 1) * LD + 8 * cb + g] = lacc[cb][nb][1];
                     }
-                asm volatile("bar.sync 1, %0;" ::"n"(PT_CONSUMERS * 32) : "memory");
-                double* lp = prm.Lpart + (size_t)panel * prm.ldlp * RT;
-#pragma unroll
-                for (int i = 0; i < (PT_TJ * RT) / (PT_CONSUMERS * 32); ++i) {
-                    const int e = tid + i * PT_CONSUMERS * 32;
-                    double sum = 0.0;
-#pragma unroll
-                    for (int w = 0; w < PT_CONSUMERS; ++w) sum += lred[(size_t)w * PT_TJ * RT + e];
-                    const int c = e / PT_TJ, j = e % PT_TJ;
-                    const int64_t col = (int64_t)jt * PT_TJ + j;
-                    if (col < prm.m) lp[col + (int64_t)c * prm.ldlp] = sum;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(PT_CONSUMERS * 32) : "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(lfull);
             }
         }
         if (DO_K) {
@@ -332,7 +348,7 @@ inline void launch_pass(dlra_engine* e, const Delta& d, int rc, const double* Vf
     CUtensorMap mapA = make_map_2d(d.A, e->n, e->m, d.lda, 16, PT_TJ, true);
     CUtensorMap mapP = DIFF ? make_map_2d(d.Aprev, e->n, e->m, d.ldap, 16, PT_TJ, true) : mapA;
     CUtensorMap mapU = DO_L ? make_map_2d(Uf, e->n, rc, ldu, 16, RT, true) : mapA;
-    CUtensorMap mapV = DO_K ? make_map_2d(Vf, e->m, rc, ldv, PT_TJ, RT, false) : mapA;
+    CUtensorMap mapV = DO_K ? make_map_2d(Vf, e->m, rc, ldv, 16, RT, true) : mapA;
     PassParams prm;
     prm.n = e->n; prm.m = e->m; prm.rc = rc; prm.nsub = nsub; prm.npanels = npanels; prm.ntj = (int)cdiv(e->m, PT_TJ);
     prm.K = K; prm.ldk = ldk; prm.Kin = nullptr; prm.Lpart = Lpart; prm.ldlp = ldlp;
