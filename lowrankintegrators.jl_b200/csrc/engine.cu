@@ -51,6 +51,10 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         e->cx.num_sms = prop.multiProcessorCount;
         DLRA_CUDA(cudaStreamCreateWithFlags(&e->cx.stream, cudaStreamNonBlocking));
         DLRA_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+        DLRA_CUDA(cudaStreamCreateWithFlags(&e->ax.stream, cudaStreamNonBlocking));
+        e->ax.num_sms = e->cx.num_sms;
+        DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+        DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         const int64_t W = e->W;
         auto dmalloc = [&](int64_t doubles) {
             double* p = nullptr;
@@ -66,8 +70,9 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         e->S = sb; sb += W * W; e->M = sb; sb += W * W; e->N = sb; sb += W * W; e->Sh = sb; sb += W * W;
         e->T1 = sb; sb += W * W; e->T2 = sb; sb += W * W; e->Rm = sb; sb += W * W; e->Pm = sb; sb += W * W;
         e->Qm = sb; sb += W * W; e->sig = sb; sb += W; e->scal_dev = sb + W;
-        DLRA_CUDA(cudaMalloc(&e->cx.counters, 256 * sizeof(unsigned int)));
-        DLRA_CUDA(cudaMemsetAsync(e->cx.counters, 0, 256 * sizeof(unsigned int), e->cx.stream));
+        DLRA_CUDA(cudaMalloc(&e->cx.counters, 512 * sizeof(unsigned int)));
+        DLRA_CUDA(cudaMemsetAsync(e->cx.counters, 0, 512 * sizeof(unsigned int), e->cx.stream));
+        e->ax.counters = e->cx.counters + 256;
         DLRA_CUDA(cudaMalloc(&e->r_new_dev, sizeof(int)));
         DLRA_CUDA(cudaHostAlloc(&e->r_new_host, sizeof(int), cudaHostAllocDefault));
         *e->r_new_host = r0;
@@ -91,6 +96,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     if (!h) return DLRA_OK;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->cx.stream);
+    cudaStreamSynchronize(h->ax.stream);
     cudaStreamSynchronize(h->copy_stream);
     h->comm.destroy();
     cudaFree(h->U); cudaFree(h->UB); cudaFree(h->V); cudaFree(h->VB); cudaFree(h->small_block);
@@ -100,7 +106,9 @@ extern "C" int dlra_destroy(dlra_handle h) {
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int i = 0; i < 8; ++i) if (h->user_events[i]) cudaEventDestroy(h->user_events[i]);
     de_release(h);
-    cudaStreamDestroy(h->cx.stream); cudaStreamDestroy(h->copy_stream);
+    h->gws2.release(); h->tws2.release(); h->wtmp2.release();
+    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+    cudaStreamDestroy(h->cx.stream); cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->ax.stream);
     delete h;
     return DLRA_OK;
 }
@@ -281,23 +289,40 @@ static void end_data_step(dlra_handle h) {
 // ---------------------------------------------------------------------------------------------------
 // shared step pieces
 // ---------------------------------------------------------------------------------------------------
-static void ensure_qr_ws(dlra_handle h, int64_t rows, int C) {
+// scratch set of a stream: main (n-side and everything sequential) or auxiliary (replicated m-side chain)
+struct Side {
+    Ctx* cx; DevBuf* tws; DevBuf* gws; DevBuf* wtmp;
+};
+static Side main_side(dlra_handle h) { return Side{&h->cx, &h->tws, &h->gws, &h->wtmp}; }
+static Side aux_side(dlra_handle h) { return Side{&h->ax, &h->tws2, &h->gws2, &h->wtmp2}; }
+// the auxiliary stream starts after everything enqueued so far on the main stream ...
+static void fork_aux(dlra_handle h) {
+    DLRA_CUDA(cudaEventRecord(h->ev_fork, h->cx.stream));
+    DLRA_CUDA(cudaStreamWaitEvent(h->ax.stream, h->ev_fork, 0));
+}
+// ... and the main stream continues once the auxiliary chain is done
+static void join_aux(dlra_handle h) {
+    DLRA_CUDA(cudaEventRecord(h->ev_join, h->ax.stream));
+    DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->ev_join, 0));
+}
+static void ensure_qr_ws(Side sd, int64_t rows, int C) {
     const int cb = std::min(C, TSQR_MAXC);
-    h->tws.ensure(tsqr_ws_size(rows, cb, 8), h->cx.stream);
+    sd.tws->ensure(tsqr_ws_size(rows, cb, 8), sd.cx->stream);
     if (C > TSQR_MAXC) {
-        h->wtmp.ensure(thin_qr_wtmp(C), h->cx.stream);
-        h->gws.ensure(gemm_tn_ws(h->cx, rows, C, TSQR_MAXC), h->cx.stream);
+        sd.wtmp->ensure(thin_qr_wtmp(C), sd.cx->stream);
+        sd.gws->ensure(gemm_tn_ws(*sd.cx, rows, C, TSQR_MAXC), sd.cx->stream);
     }
 }
 // thin QR of an n-side (row sharded) matrix, in place
 static void qr_nside(dlra_handle h, double* A, int C, double* R) {
-    ensure_qr_ws(h, h->n, C);
+    Side sd = main_side(h);
+    ensure_qr_ws(sd, h->n, C);
     thin_qr(h->cx, h->comm, h->n, C, A, h->n, A, h->n, R, h->W, h->tws.p, h->gws.p, h->wtmp.p);
 }
 // thin QR of an m-side (replicated) matrix, in place, computed redundantly on every rank
-static void qr_mside(dlra_handle h, double* A, int C, double* R) {
-    ensure_qr_ws(h, h->m, C);
-    thin_qr(h->cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, h->tws.p, h->gws.p, h->wtmp.p);
+static void qr_mside(dlra_handle h, Side sd, double* A, int C, double* R) {
+    ensure_qr_ws(sd, h->m, C);
+    thin_qr(*sd.cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, sd.tws->p, sd.gws->p, sd.wtmp->p);
 }
 // C (p x q, ld W) = A' * B over the sharded n dimension (+ all-reduce)
 static void gram_nside(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
@@ -311,9 +336,9 @@ static void gram_nside(dlra_handle h, int p, int q, const double* A, const doubl
         gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, C, h->W, 1.0, 0.0, h->gws.p);
     }
 }
-static void gram_mside(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
-    h->gws.ensure(gemm_tn_ws(h->cx, h->m, p, q), h->cx.stream);
-    gemm_tn(h->cx, h->m, p, q, A, h->m, nullptr, 0, B, h->m, C, h->W, 1.0, 0.0, h->gws.p);
+static void gram_mside(dlra_handle h, Side sd, int p, int q, const double* A, const double* B, double* C) {
+    sd.gws->ensure(gemm_tn_ws(*sd.cx, h->m, p, q), sd.cx->stream);
+    gemm_tn(*sd.cx, h->m, p, q, A, h->m, nullptr, 0, B, h->m, C, h->W, 1.0, 0.0, sd.gws->p);
 }
 // dense m x r all-reduce of an m-side matrix with ld == m
 static void allreduce_mside(dlra_handle h, double* L, int r) { h->comm.allreduce_sum(L, h->m * (int64_t)r, h->cx.stream); }
@@ -352,10 +377,12 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
         de_K_flow(h, K, r, h->V, sc.t, sc.dt);
         de_L_flow(h, L, r, h->U, sc.t, sc.dt);
     }
-    qr_nside(h, K, r, nullptr);                 // U1 = qr(K).Q
-    gram_nside(h, r, r, K, h->U, h->M);         // M = U1'*U0
-    qr_mside(h, L, r, nullptr);                 // V1 = qr(L).Q
-    gram_mside(h, r, r, L, h->V, h->N);         // N = V1'*V0
+    fork_aux(h);                                          // m-side chain on the auxiliary stream ...
+    qr_mside(h, aux_side(h), L, r, nullptr);              // V1 = qr(L).Q
+    gram_mside(h, aux_side(h), r, r, L, h->V, h->N);      // N = V1'*V0
+    qr_nside(h, K, r, nullptr);                           // ... overlaps U1 = qr(K).Q
+    gram_nside(h, r, r, K, h->U, h->M);                   // M = U1'*U0
+    join_aux(h);
     small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);   // T1 = M*S0
     small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);   // Sh = M*S0*N'
     if (sc.is_data) {
@@ -386,7 +413,7 @@ static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
         // W = ΔA'*U1 ; S~ = R − W'*V0 ; L = V0*S~' + W        (U1'ΔA V0 == W'V0)
         pass_KL(h, sc.d, r, nullptr, 0, K, n, nullptr, 0, L, m);
         allreduce_mside(h, L, r);
-        gram_mside(h, r, r, L, h->V, h->T1);                                                  // T1 = W'*V0
+        gram_mside(h, main_side(h), r, r, L, h->V, h->T1);                                    // T1 = W'*V0
         copy_mat(cx, r, r, h->Rm, W, false, h->Sh, W);
         copy_mat(cx, r, r, h->T1, W, false, h->Sh, W, -1.0, 1.0);                             // Sh = R − W'V0
         gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->Sh, W, true, L, m, 1.0, 1.0);            // L = W + V0*Sh'
@@ -396,7 +423,7 @@ static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
         gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->Sh, W, true, L, m, 1.0, 0.0);            // L0 = V0*S~'
         de_L_flow(h, L, r, K, sc.t, sc.dt);
     }
-    qr_mside(h, L, r, h->Rm);                                                                 // V1, R_L
+    qr_mside(h, main_side(h), L, r, h->Rm);                                                   // V1, R_L
     copy_mat(cx, r, r, h->Rm, W, true, h->S, W);                                              // S1 = R_L'
     std::swap(h->U, h->UB);
     std::swap(h->V, h->VB);
@@ -415,7 +442,7 @@ static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
         gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 0.0);
         de_L_flow(h, L, r, h->U, sc.t, sc.dt);
     }
-    qr_mside(h, L, r, h->Rm);                                                                 // V1, R_L
+    qr_mside(h, main_side(h), L, r, h->Rm);                                                   // V1, R_L
     copy_mat(cx, r, r, h->Rm, W, true, h->Sh, W);                                             // Sh = R_L'
     if (sc.is_data) {
         // Wn = ΔA*V1 ; S~ = R_L' − U0'*Wn ; K = U0*S~ + Wn
@@ -461,10 +488,12 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     }
     copy_mat(cx, n, r, h->U, n, false, Kh + (int64_t)r * n, n);          // Uhat[:, r+1:end] = U0
     copy_mat(cx, m, r, h->V, m, false, Lh + (int64_t)r * m, m);
+    fork_aux(h);
+    qr_mside(h, aux_side(h), Lh, r2, nullptr);
+    gram_mside(h, aux_side(h), r2, r, Lh, h->V, h->N);                   // N = Vhat'*V0
     qr_nside(h, Kh, r2, nullptr);
     gram_nside(h, r2, r, Kh, h->U, h->M);                                // M = Uhat'*U0 (2r x r)
-    qr_mside(h, Lh, r2, nullptr);
-    gram_mside(h, r2, r, Lh, h->V, h->N);                                // N = Vhat'*V0
+    join_aux(h);
     small_gemm(cx, r2, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);
     small_gemm(cx, r2, r2, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);
     if (sc.is_data) {
@@ -501,8 +530,10 @@ static void greedy_step(dlra_handle h, const Delta& x) {
     fill_mat(cx, n, r, XV, n, 0.0, 0.0);
     pass_KL(h, x, r, h->V, m, h->U, n, XV, n, XU, m);        // XV = X*V ; XU = X'*U
     allreduce_mside(h, XU, r);
+    fork_aux(h);
+    qr_mside(h, aux_side(h), XU, r, nullptr);
     qr_nside(h, XV, r, nullptr);
-    qr_mside(h, XU, r, nullptr);
+    join_aux(h);
     pass_S(h, x, r, r, XV, n, XU, m, h->T1, W);              // S = U1'*X*V1
     allreduce_small(h, h->T1, r, r);
     copy_mat(cx, r, r, h->T1, W, false, h->S, W);
@@ -643,12 +674,12 @@ extern "C" int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass
     }
     h->pass_events.clear();
     h->pass_event_kind.clear();
-    if (kernel_launches) *kernel_launches = h->cx.launches;
+    if (kernel_launches) *kernel_launches = h->cx.launches + h->ax.launches;
     if (pass_launches) *pass_launches = h->pass_launches;
     if (pass_ms_total) *pass_ms_total = h->pass_ms;
     if (pass_bytes_total) *pass_bytes_total = h->pass_bytes;
     if (reset) {
-        h->cx.launches = 0; h->pass_launches = 0; h->pass_ms = 0.0; h->pass_bytes = 0.0;
+        h->cx.launches = 0; h->ax.launches = 0; h->pass_launches = 0; h->pass_ms = 0.0; h->pass_bytes = 0.0;
         for (int i = 0; i < 3; ++i) { h->kind_launches[i] = 0; h->kind_ms[i] = 0; h->kind_bytes[i] = 0; h->kind_flops[i] = 0; }
     }
     DLRA_API_END(h)

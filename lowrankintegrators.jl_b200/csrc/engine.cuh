@@ -60,6 +60,8 @@ struct dlra_engine {
     int r = 0, rmax = 0, flags = 0;
     int W = 0;                  // widest factor block (rmax, or 2*rmax when rank adaptive)
     dlra::Ctx cx;
+    dlra::Ctx ax;               // auxiliary stream: the replicated m-side chain (QR(L), N) overlaps the n-side chain (QR(K), M)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     dlra::Comm comm;            // row-shard communicator
     dlra::Comm self;            // nranks = 1: for replicated (m-side) factorizations
     cudaStream_t copy_stream = nullptr;
@@ -74,6 +76,7 @@ struct dlra_engine {
     int* r_new_host = nullptr;  // pinned, mapped
     double* scal_dev = nullptr; // 8 doubles of device scalars
     dlra::DevBuf gws, tws, wtmp, jws, nscr, mscr, part;  // grow-on-demand scratch
+    dlra::DevBuf gws2, tws2, wtmp2;                       // scratch of the auxiliary stream
 
     // data feed
     const double* prev = nullptr; int64_t ldprev = 0;

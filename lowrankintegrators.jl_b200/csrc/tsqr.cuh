@@ -227,6 +227,37 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows,
     }
 }
 
+// rows <= 128: one warp factors the whole matrix (used for the top of the tree and for all-gathered R stacks)
+template <int CP>
+__global__ void __launch_bounds__(32, 1) tsqr_small_kernel(int rows, int C, const double* __restrict__ A, int64_t lda,
+                                                          double* __restrict__ Q, int64_t ldq, double* __restrict__ Rout, int64_t ldr) {
+    constexpr int RPL = 4;
+    __shared__ double vs[CP][32 * RPL];
+    __shared__ double taus[CP];
+    const int lane = threadIdx.x;
+    double a[RPL][CP];
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            const int g = lane + 32 * q;
+            a[q][c] = (g < rows && c < C) ? A[g + (int64_t)c * lda] : 0.0;
+        }
+    reg_panel_qr<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane);
+    if (lane < CP) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) Rout[lane + (int64_t)c * ldr] = (lane <= c) ? vs[c][lane] : 0.0;
+    }
+    reg_panel_formq<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane);
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) {
+            const int g = lane + 32 * q;
+            if (g < rows && c < C) Q[g + (int64_t)c * ldq] = a[q][c];
+        }
+}
+
 // Q[rows of block b, :C] <- Q[block b, :C] * X_b[:C,:C],  X_b = Xstack[b*xstride .. , :] (ldx); block = block_rows rows.
 template <int CP>
 __global__ void __launch_bounds__(128) apply_blocks_kernel(int64_t rows, int C, double* __restrict__ Q, int64_t ldq, int64_t block_rows,
@@ -270,6 +301,13 @@ inline int64_t tsqr_ws_size(int64_t rows, int C, int nranks) {
 }
 
 inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* Rstack, int64_t ldr) {
+    if (rows <= 128) {
+        if (CP == 8) tsqr_small_kernel<8><<<1, 32, 0, cx.stream>>>((int)rows, C, A, lda, Q, ldq, Rstack, ldr);
+        else tsqr_small_kernel<16><<<1, 32, 0, cx.stream>>>((int)rows, C, A, lda, Q, ldq, Rstack, ldr);
+        cx.launches++;
+        DLRA_CUDA(cudaGetLastError());
+        return;
+    }
     const unsigned nb = (unsigned)cdiv(rows, TSQR_BR);
     static bool attr_set = false;
     if (!attr_set) {
