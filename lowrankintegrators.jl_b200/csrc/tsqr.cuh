@@ -27,109 +27,143 @@ constexpr int TSQR_RPL0 = 4;    // rows per lane at level 0 (128-row panels)
 constexpr int TSQR_BR = TSQR_NW * 32 * TSQR_RPL0;  // 1024 rows per CTA
 constexpr int TSQR_MAXC = 16;
 
+// Transposing warp reduction: N (power of two) per-lane partial sums -> the warp total of value i ends up on the lanes
+// with (lane >> log2(32/N)) == i.  Costs N-1 + log2(32/N) shuffles instead of 5*N for N separate butterflies.
+template <int N, int OFF>
+struct TReduce {
+    static __device__ __forceinline__ double run(double (&e)[N], int lane) {
+        double f[N / 2];
+        const bool up = (lane & OFF) != 0;
+#pragma unroll
+        for (int i = 0; i < N / 2; ++i) {
+            const double keep = up ? e[i + N / 2] : e[i];
+            const double send = up ? e[i] : e[i + N / 2];
+            f[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+        }
+        return TReduce<N / 2, OFF / 2>::run(f, lane);
+    }
+};
+template <int OFF>
+struct TReduce<1, OFF> {
+    static __device__ __forceinline__ double run(double (&e)[1], int) {
+        double h = e[0];
+#pragma unroll
+        for (int o = OFF; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+        return h;
+    }
+};
+
 // Householder QR of a (32*RPL) x CP register panel: lane l holds rows l + 32 q.  The loop over columns is a REAL loop
-// (compact code: a fully unrolled factorisation is instruction-fetch bound): the register columns are rotated so the
-// pivot column is always a[.][0]; the finished column j (R above/on the diagonal, the Householder vector below it,
-// unit diagonal implicit) is parked in shared memory `vs` ([CP][VLD], lane <-> row), tau[] as LAPACK dlarfg.
+// (compact code: a fully unrolled factorisation is instruction-fetch bound) that handles two pivot columns per trip and
+// then rotates the register columns by two, so the pivots are always positions 0 and 1.  The finished column j (R above/on
+// the diagonal, the Householder vector below it, unit diagonal implicit) is parked in shared memory `vs` ([CP][vld],
+// lane <-> row), tau[] as LAPACK dlarfg.  One transposing reduction per column yields the norm and all trailing dots.
 template <int CP, int RPL>
 __device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, int vld, double* tau_s, int lane) {
+    constexpr int SH = (CP == 16) ? 1 : 2;   // owner lane of reduced value i is i << SH
 #pragma unroll 1
-    for (int j = 0; j < CP; ++j) {
-        double e[CP];
+    for (int j0 = 0; j0 < CP; j0 += 2) {
+        static_for<0, 2>([&](auto PP) {
+            constexpr int P = decltype(PP)::value;
+            const int j = j0 + P;
+            double xm[RPL];
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            double s = 0.0;
+            for (int q = 0; q < RPL; ++q) xm[q] = ((q > 0) || (lane > j)) ? a[q][P] : 0.0;
+            double e[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                double s = 0.0;
+                if (c + P < CP) {
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) s = fma(xm[q], a[q][c + P], s);
+                }
+                e[c] = s;
+            }
+            const double h = TReduce<CP, 16>::run(e, lane);
+            const double alpha = __shfl_sync(0xffffffffu, a[0][P], j);
+            const double ss = __shfl_sync(0xffffffffu, h, 0);
+            double t = 0.0, scale = 0.0, beta = alpha;
+            if (ss > 0.0) {
+                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+                t = (beta - alpha) / beta;
+                scale = 1.0 / (alpha - beta);
+            }
+            if (lane == 0) tau_s[j] = t;
+            double vm[RPL];
 #pragma unroll
             for (int q = 0; q < RPL; ++q) {
-                const bool act = (q > 0) || (lane > j);
-                s = act ? fma(a[q][0], a[q][c], s) : s;
+                vm[q] = xm[q] * scale;
+                a[q][P] = ((q > 0) || (lane > j)) ? vm[q] : a[q][P];
             }
-            e[c] = s;
-        }
+            if (lane == j) { a[0][P] = beta; vm[0] = 1.0; }
 #pragma unroll
-        for (int c = 0; c < CP; ++c) e[c] = warp_sum(e[c]);
-        const double alpha = __shfl_sync(0xffffffffu, a[0][0], j);
-        const double ss = e[0];
-        double t = 0.0, scale = 0.0, beta = alpha;
-        if (ss > 0.0) {
-            beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-            t = (beta - alpha) / beta;
-            scale = 1.0 / (alpha - beta);
-        }
-        if (lane == 0) tau_s[j] = t;
+            for (int q = 0; q < RPL; ++q) vs[j * vld + lane + 32 * q] = a[q][P];
+            // apply H_j to the trailing columns
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) {
-            const bool act = (q > 0) || (lane > j);
-            a[q][0] = act ? a[q][0] * scale : a[q][0];
-        }
-        a[0][0] = (lane == j) ? beta : a[0][0];
+            for (int c = P + 1; c < CP; ++c) {
+                const double arow = __shfl_sync(0xffffffffu, a[0][c], j);
+                const double ec = __shfl_sync(0xffffffffu, h, (c - P) << SH);
+                const double w = (arow + ec * scale) * t;
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) vs[j * vld + lane + 32 * q] = a[q][0];
-        // apply H_j to the trailing columns and rotate them one position to the left
-#pragma unroll
-        for (int c = 1; c < CP; ++c) {
-            const double arow = __shfl_sync(0xffffffffu, a[0][c], j);
-            const double w = (arow + e[c] * scale) * t;
-#pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                const bool act = (q > 0) || (lane > j);
-                double x = a[q][c];
-                x = act ? fma(-w, a[q][0], x) : x;
-                if (q == 0) x = (lane == j) ? x - w : x;
-                a[q][c] = x;
+                for (int q = 0; q < RPL; ++q) a[q][c] = fma(-w, vm[q], a[q][c]);
             }
-        }
+        });
+        // rotate two positions to the left
 #pragma unroll
-        for (int c = 1; c < CP; ++c)
+        for (int c = 2; c < CP; ++c)
 #pragma unroll
-            for (int q = 0; q < RPL; ++q) a[q][c - 1] = a[q][c];
+            for (int q = 0; q < RPL; ++q) a[q][c - 2] = a[q][c];
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) a[q][CP - 1] = 0.0;
+        for (int q = 0; q < RPL; ++q) { a[q][CP - 2] = 0.0; a[q][CP - 1] = 0.0; }
     }
     __syncwarp();
 }
 
-// Explicit thin Q (32*RPL x CP) into registers from the vectors parked by reg_panel_qr (LAPACK dorg2r recurrence, looped
-// with rotating register columns: position c holds Q column j+1+c-1 while column j is being built).
+// Explicit thin Q (32*RPL x CP) into registers from the vectors parked by reg_panel_qr (LAPACK dorg2r recurrence, looped,
+// two columns per trip with rotating register columns: position c holds Q column j_low + c).
 template <int CP, int RPL>
 __device__ __forceinline__ void reg_panel_formq(double (&a)[RPL][CP], const double* vs, int vld, const double* tau_s, int lane) {
+    constexpr int SH = (CP == 16) ? 1 : 2;
 #pragma unroll
     for (int c = 0; c < CP; ++c)
 #pragma unroll
         for (int q = 0; q < RPL; ++q) a[q][c] = 0.0;
 #pragma unroll 1
-    for (int j = CP - 1; j >= 0; --j) {
-        const double t = tau_s[j];
-        double v[RPL];
+    for (int j0 = CP - 2; j0 >= 0; j0 -= 2) {
+        // rotate two positions to the right: room for columns j0 (position 0) and j0+1 (position 1)
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) {
-            const bool act = (q > 0) || (lane > j);
-            v[q] = act ? vs[j * vld + lane + 32 * q] : 0.0;
-        }
-        // rotate right: make room for column j at position 0
+        for (int c = CP - 1; c >= 2; --c)
 #pragma unroll
-        for (int c = CP - 1; c >= 1; --c)
+            for (int q = 0; q < RPL; ++q) a[q][c] = a[q][c - 2];
+        static_for<0, 2>([&](auto PP) {
+            constexpr int P = 1 - decltype(PP)::value;   // position 1 (column j0+1) first, then position 0 (column j0)
+            const int j = j0 + P;
+            const double t = tau_s[j];
+            double vm[RPL];
 #pragma unroll
-            for (int q = 0; q < RPL; ++q) a[q][c] = a[q][c - 1];
+            for (int q = 0; q < RPL; ++q) vm[q] = ((q > 0) || (lane > j)) ? vs[j * vld + lane + 32 * q] : 0.0;
+            double e[CP];
 #pragma unroll
-        for (int c = 1; c < CP; ++c) {
-            double s = 0.0;
+            for (int c = 0; c < CP; ++c) {
+                double s = 0.0;
+                if (c + P + 1 < CP) {
 #pragma unroll
-            for (int q = 0; q < RPL; ++q) s = fma(v[q], a[q][c], s);
-            const double w = warp_sum(s) * t;   // Q[j][c] == 0 before H_j is applied
-#pragma unroll
-            for (int q = 0; q < RPL; ++q) {
-                double x = fma(-w, v[q], a[q][c]);
-                if (q == 0) x = (lane == j) ? -w : x;
-                a[q][c] = x;
+                    for (int q = 0; q < RPL; ++q) s = fma(vm[q], a[q][c + P + 1], s);
+                }
+                e[c] = s;
             }
-        }
+            const double h = TReduce<CP, 16>::run(e, lane);
+            if (lane == j) vm[0] = 1.0;    // row j of the finished columns is still 0: the same FMA writes -w there
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) {
-            double x = -t * v[q];
-            if (q == 0) x = (lane == j) ? 1.0 - t : x;
-            a[q][0] = x;
-        }
+            for (int c = P + 1; c < CP; ++c) {
+                const double w = __shfl_sync(0xffffffffu, h, (c - P - 1) << SH) * t;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) a[q][c] = fma(-w, vm[q], a[q][c]);
+            }
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) a[q][P] = -t * vm[q];
+            if (lane == j) a[0][P] = 1.0 - t;
+        });
     }
 }
 
