@@ -26,7 +26,7 @@ constexpr int PT_SI = 64;        // rows per stage
 constexpr int PT_TJ = 32;        // columns per stage
 constexpr int PT_NSUB_MAX = 7;   // stages (row sub-tiles) per panel held in K accumulators
 constexpr int PT_CONSUMERS = 8;  // consumer warps
-constexpr int PT_THREADS = (PT_CONSUMERS + 2) * 32;   // + TMA producer warp + L-reducer warp
+constexpr int PT_THREADS = (PT_CONSUMERS + 4) * 32;   // + one service warpgroup: TMA producer warp, L-reducer warp, 2 idle
 constexpr int PT_LRED_LD = PT_TJ + 2;                 // padded column stride of the L reduction buffer (conflict-free)
 constexpr int PT_TBYTES = PT_SI * PT_TJ * 8;  // 16 KB
 constexpr int PT_BOXBYTES = 16 * PT_TJ * 8;   // 4 KB: one 16-row box
@@ -87,6 +87,9 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     __syncthreads();
 
     const int nsub = prm.nsub;
+    // register re-partitioning (sm_90+ setmaxnreg): the service warpgroup gives its registers to the two consumer warpgroups
+    if (warp >= PT_CONSUMERS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     if (warp == PT_CONSUMERS) {
         // ------------------------------ producer: one elected lane drives the TMA engine -------------------
         if (lane == 0) {
@@ -156,6 +159,9 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
         return;
     }
+    return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
 
     // ---------------------------------- consumers: 8 warps, DMMA ------------------------------------------
     const int g = lane >> 2, k = lane & 3;
@@ -377,6 +383,14 @@ inline void launch_pass_rt(dlra_engine* e, const Delta& d, int rc, const double*
 #undef DLRA_PASS_CASE
 }
 
+// K-only launches also exist with 32 factor columns per chunk (K accumulators + V fragments still fit the register file):
+// at r = 32 a K-only pass is HBM-bound again, so one sweep instead of two halves its time.
+inline void launch_pass_k32(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, double* K, int64_t ldk, int nsub,
+                            int npanels) {
+    if (d.Aprev) launch_pass<32, true, false, true>(e, d, rc, Vf, ldv, nullptr, 0, K, ldk, nullptr, 0, nsub, npanels);
+    else launch_pass<32, true, false, false>(e, d, rc, Vf, ldv, nullptr, 0, K, ldk, nullptr, 0, nsub, npanels);
+}
+
 // K (n x r) += ΔA·Vf and/or Lout (m x r, ldl) = ΔAᵀ·Uf, r processed in chunks of 16 (8 for a narrow tail)
 inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
                         double* K, int64_t ldk, double* Lout, int64_t ldl) {
@@ -386,7 +400,13 @@ inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf,
     const int npanels = (int)cdiv(cdiv(e->n, PT_SI), nsub);
     const int64_t ldlp = round_up(e->m, 2);
     if (Lout) e->part.ensure((int64_t)npanels * ldlp * 16, e->cx.stream);
-    for (int c0 = 0; c0 < r; c0 += 16) {
+    for (int c0 = 0; c0 < r;) {
+        if (K && !Lout && r - c0 > 16) {   // wide K-only chunk
+            const int rc32 = std::min(32, r - c0);
+            launch_pass_k32(e, d, rc32, Vf + (int64_t)c0 * ldv, ldv, K + (int64_t)c0 * ldk, ldk, nsub, npanels);
+            c0 += rc32;
+            continue;
+        }
         const int rc = std::min(16, r - c0);
         double* Kc = K ? K + (int64_t)c0 * ldk : nullptr;
         double* Lp = Lout ? e->part.p : nullptr;
@@ -399,6 +419,7 @@ inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf,
             launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
             if (Lout) reduce_parts(e->cx, (int)e->m, rc, npanels, Lp, ldlp, ldlp * 16, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
         }
+        c0 += rc;
     }
 }
 
