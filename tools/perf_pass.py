@@ -11,6 +11,7 @@ def main():
     r = int(sys.argv[3]) if len(sys.argv) > 3 else 16
     steps = int(sys.argv[4]) if len(sys.argv) > 4 else 10
     algs = sys.argv[5].split(",") if len(sys.argv) > 5 else ["bug", "ksl", "rabug", "greedy"]
+    kinds = sys.argv[6].split(",") if len(sys.argv) > 6 else ["delta", "snapshot"]
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev); g.manual_seed(0)
     snaps = [lri.empty_colmajor(n, m, dev) for _ in range(3)]
@@ -21,6 +22,7 @@ def main():
     for alg in algs:
         for kind, kname in ((L.DATA_DELTA, "delta"), (L.DATA_SNAPSHOT, "snapshot")):
             if alg == "greedy" and kind == L.DATA_DELTA: continue
+            if kname not in kinds: continue
             eng = lri.Engine(n, m, r, rmax=r, rank_adaptive=(alg == "rabug"))
             eng.set_factors(U0, S0, V0)
             eng.data_init(snaps[0])
