@@ -39,7 +39,7 @@ struct PassParams {
     int ntj;         // column tiles
     double* K; int64_t ldk;       // K-use output (+=), may be null
     const double* Kin;            // unused
-    double* Lpart; int64_t ldlp;  // [npanels][ldlp x RT] partial L (ldlp >= m), may be null
+    double* Lpart; int64_t ldlp;  // [gridDim.x][ldlp x RT] per-CTA partial L (ldlp >= m), may be null
 };
 
 template <int RT, bool DO_K, bool DO_L, bool DIFF>
@@ -89,7 +89,7 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int nsub = prm.nsub;
     // register re-partitioning (sm_90+ setmaxnreg): the service warpgroup gives its registers to the two consumer warpgroups
     if (warp >= PT_CONSUMERS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     if (warp == PT_CONSUMERS) {
         // ------------------------------ producer: one elected lane drives the TMA engine -------------------
         if (lane == 0) {
@@ -139,17 +139,24 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         // ------------------------------ L reducer: sums the 8 consumer warps' partial L tiles off the critical path ---
         if (DO_L) {
             uint32_t ph = 0;
+            // one partial per CTA: the first panel stores, later panels of this CTA accumulate (fixed order => deterministic)
+            double* lp = prm.Lpart + (size_t)blockIdx.x * prm.ldlp * RT;
             for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
-                double* lp = prm.Lpart + (size_t)panel * prm.ldlp * RT;
+                const bool first = (panel == (int)blockIdx.x);
                 for (int jt = 0; jt < prm.ntj; ++jt) {
+                    const int64_t col = (int64_t)jt * PT_TJ + lane;
+                    const bool okc = col < prm.m;
+                    double prev[RT];
+                    // the previous panels' running sum is fetched BEFORE waiting for the consumers (latency fully hidden)
+#pragma unroll
+                    for (int i = 0; i < RT; ++i) prev[i] = (!first && okc) ? __ldcg(lp + col + (int64_t)i * prm.ldlp) : 0.0;
                     mbar_wait(lfull, ph);
-#pragma unroll 4
+#pragma unroll
                     for (int i = 0; i < RT; ++i) {   // element (c = i, j = lane)
-                        double sum = 0.0;
+                        double sum = prev[i];
 #pragma unroll
                         for (int w = 0; w < PT_CONSUMERS; ++w) sum += lred[(size_t)w * LD * RT + i * LD + lane];
-                        const int64_t col = (int64_t)jt * PT_TJ + lane;
-                        if (col < prm.m) lp[col + (int64_t)i * prm.ldlp] = sum;
+                        if (okc) __stcg(lp + col + (int64_t)i * prm.ldlp, sum);
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(lfree);
@@ -161,7 +168,7 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     }
     return;
     }
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
 
     // ---------------------------------- consumers: 8 warps, DMMA ------------------------------------------
     const int g = lane >> 2, k = lane & 3;
@@ -399,7 +406,8 @@ inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf,
     const int nsub = choose_nsub(e->n, e->cx.num_sms);
     const int npanels = (int)cdiv(cdiv(e->n, PT_SI), nsub);
     const int64_t ldlp = round_up(e->m, 2);
-    if (Lout) e->part.ensure((int64_t)npanels * ldlp * 16, e->cx.stream);
+    const int nparts = std::min(npanels, e->cx.num_sms);   // == grid size of the pass kernel
+    if (Lout) e->part.ensure((int64_t)nparts * ldlp * 16, e->cx.stream);
     for (int c0 = 0; c0 < r;) {
         if (K && !Lout && r - c0 > 16) {   // wide K-only chunk
             const int rc32 = std::min(32, r - c0);
@@ -414,10 +422,10 @@ inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf,
         const double* Uc = Uf ? Uf + (int64_t)c0 * ldu : nullptr;
         if (rc <= 8) {
             launch_pass_rt<8>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
-            if (Lout) reduce_parts(e->cx, (int)e->m, rc, npanels, Lp, ldlp, ldlp * 8, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
+            if (Lout) reduce_parts(e->cx, (int)e->m, rc, nparts, Lp, ldlp, ldlp * 8, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
         } else {
             launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
-            if (Lout) reduce_parts(e->cx, (int)e->m, rc, npanels, Lp, ldlp, ldlp * 16, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
+            if (Lout) reduce_parts(e->cx, (int)e->m, rc, nparts, Lp, ldlp, ldlp * 16, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
         }
         c0 += rc;
     }
