@@ -191,9 +191,7 @@ def run_gpu(args):
     def make_engine():
         eng = lri.Engine(n, m, r, rmax=r, device=local_rank)
         if world > 1:
-            box = [lri.Engine.nccl_unique_id() if rank == 0 else None]
-            dist.broadcast_object_list(box, src=0)
-            eng.comm_init(world, rank, box[0])
+            lri.attach_engine(eng)   # P2P (CUDA IPC over NVLink) by default, DLRA_COMM=nccl for the NCCL transport
         eng.set_factors(U0, S0, V0)
         return eng
 

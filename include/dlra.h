@@ -85,7 +85,11 @@ const char* dlra_version(void);
 /* ---- multi-GPU (no counterpart in the single-process reference) ---------------- */
 int dlra_nccl_unique_id(void* id128);                       /* 128-byte ncclUniqueId, made on rank 0 */
 int dlra_comm_init(dlra_handle h, int nranks, int rank, const void* id128);
-/* caller-provided collectives (testing on CPU-less NCCL setups): not used in production */
+/* Peer-to-peer transport (preferred on one NVSwitch box): every rank exports the CUDA-IPC handle (64 bytes) of its
+ * exchange region, the host runtime all-gathers the handles, every rank imports all of them.  Afterwards the
+ * collectives of the step run as single kernels that read the peers' contributions over NVLink (no NCCL calls). */
+int dlra_p2p_export(dlra_handle h, void* ipc_handle64);
+int dlra_p2p_import(dlra_handle h, int nranks, int rank, const void* ipc_handles /* nranks x 64 bytes */);
 
 /* ---- factors: SVDLikeRepresentation(U,S,V) (LowRankArithmetic; README.md:85) ----------------- */
 /* deep copy in, as init() does with deepcopy(prob.u0) (projector_splitting.jl:110) */

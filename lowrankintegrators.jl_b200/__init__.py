@@ -7,7 +7,7 @@ from .api import (DLRIntegrator, DLRSolution, DualLieTrotter, GreedyIntegrator, 
                   truncate_to_tolerance, truncated_svd, update_sol)
 from .engine import Engine, colmajor_device, empty_colmajor
 from .rhs import BurgersRHS, FactoredRHS, LinearRHS
-from .distributed import comm_from_torch, row_shard
+from .distributed import attach_engine, comm_from_torch, row_shard
 
 step_ = step  # `step!`
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -34,6 +34,8 @@ SIGNATURES = {
     "dlra_version": (C.c_char_p, []),
     "dlra_nccl_unique_id": (C.c_int, [C.c_void_p]),
     "dlra_comm_init": (C.c_int, [handle_t, C.c_int, C.c_int, C.c_void_p]),
+    "dlra_p2p_export": (C.c_int, [handle_t, C.c_void_p]),
+    "dlra_p2p_import": (C.c_int, [handle_t, C.c_int, C.c_int, C.c_void_p]),
     "dlra_set_factors_host": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]),
     "dlra_set_factors": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int]),
     "dlra_get_factors_host": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_int_p]),

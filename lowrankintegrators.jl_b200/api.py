@@ -235,10 +235,10 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
         rmax = int(min(alg.rmax, 128, m // 2 if m >= 2 else 1))
         rmax = max(rmax, r0)
     eng = Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic)
-    if comm == "torch":  # one fresh ncclUniqueId per engine, handed out through torch.distributed
-        from .distributed import comm_from_torch
-        comm = comm_from_torch()
-    if comm is not None and comm[0] > 1:
+    if comm == "torch":  # torch.distributed only hands out the IPC handles / the ncclUniqueId
+        from .distributed import attach_engine
+        attach_engine(eng)
+    elif comm is not None and comm[0] > 1:
         eng.comm_init(*comm)
     eng.set_factors(u0.U, u0.S, u0.V)  # deepcopy(prob.u0)
     if isinstance(prob, MatrixDataProblem):

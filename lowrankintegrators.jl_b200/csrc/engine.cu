@@ -65,11 +65,11 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         };
         e->U = dmalloc(e->n * W); e->UB = dmalloc(e->n * W);
         e->V = dmalloc(e->m * W); e->VB = dmalloc(e->m * W);
-        e->small_block = dmalloc(10 * W * W + 64);
+        e->small_block = dmalloc(18 * W * W + 64);
         double* sb = e->small_block;
         e->S = sb; sb += W * W; e->M = sb; sb += W * W; e->N = sb; sb += W * W; e->Sh = sb; sb += W * W;
         e->T1 = sb; sb += W * W; e->T2 = sb; sb += W * W; e->Rm = sb; sb += W * W; e->Pm = sb; sb += W * W;
-        e->Qm = sb; sb += W * W; e->sig = sb; sb += W; e->scal_dev = sb + W;
+        e->Qm = sb; sb += W * W; e->stg = sb; sb += 8 * W * W; e->sig = sb; sb += W; e->scal_dev = sb + W;
         DLRA_CUDA(cudaMalloc(&e->cx.counters, 512 * sizeof(unsigned int)));
         DLRA_CUDA(cudaMemsetAsync(e->cx.counters, 0, 512 * sizeof(unsigned int), e->cx.stream));
         e->ax.counters = e->cx.counters + 256;
@@ -138,6 +138,23 @@ extern "C" int dlra_comm_init(dlra_handle h, int nranks, int rank, const void* i
     DLRA_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks && id128, "bad communicator arguments");
     DLRA_REQUIRE(nranks <= 8, "row sharding supports up to 8 ranks (one NVSwitch box)");
     if (nranks > 1) h->comm.init(nranks, rank, id128);
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_p2p_export(dlra_handle h, void* handle64) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(handle64 != nullptr, "null output");
+    // largest message: an m x W block of L (plus slack for the small r x r / R-factor messages)
+    h->comm.p2p_alloc(((size_t)h->m * h->W + 8 * (size_t)h->W * h->W + 1024) * sizeof(double));
+    h->comm.p2p_export(handle64);
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_p2p_import(dlra_handle h, int nranks, int rank, const void* handles) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(handles != nullptr, "null handles");
+    DLRA_REQUIRE(!h->rhs.set || nranks == 1, "DE right-hand sides are single-GPU");
+    h->comm.p2p_import(nranks, rank, handles);
     DLRA_API_END(h)
 }
 
@@ -330,23 +347,36 @@ static void gram_nside(dlra_handle h, int p, int q, const double* A, const doubl
     if (h->comm.nranks > 1) {
         // reduce into a dense p x q staging block so one collective suffices
         gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, h->T2, p, 1.0, 0.0, h->gws.p);
-        h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx.stream);
+        h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx);
         copy_mat(h->cx, p, q, h->T2, p, false, C, h->W);
     } else {
         gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, C, h->W, 1.0, 0.0, h->gws.p);
     }
 }
+// local (this rank's rows) part of A'*B: the cross-rank sum is deferred and merged with a later collective
+static void gram_nside_local(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
+    h->gws.ensure(gemm_tn_ws(h->cx, h->n, p, q), h->cx.stream);
+    gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, C, h->W, 1.0, 0.0, h->gws.p);
+}
+// one all-reduce for two small matrices (ld W): halves the number of cross-GPU synchronisation points per step
+static void allreduce_pair(dlra_handle h, double* A, int pa, int qa, double* B, int pb, int qb) {
+    if (h->comm.nranks <= 1) return;
+    double* st = h->stg;   // 8*W*W doubles
+    copy_mat(h->cx, pa, qa, A, h->W, false, st, pa);
+    copy_mat(h->cx, pb, qb, B, h->W, false, st + (int64_t)pa * qa, pb);
+    h->comm.allreduce_sum(st, (int64_t)pa * qa + (int64_t)pb * qb, h->cx);
+    copy_mat(h->cx, pa, qa, st, pa, false, A, h->W);
+    copy_mat(h->cx, pb, qb, st + (int64_t)pa * qa, pb, false, B, h->W);
+}
 static void gram_mside(dlra_handle h, Side sd, int p, int q, const double* A, const double* B, double* C) {
     sd.gws->ensure(gemm_tn_ws(*sd.cx, h->m, p, q), sd.cx->stream);
     gemm_tn(*sd.cx, h->m, p, q, A, h->m, nullptr, 0, B, h->m, C, h->W, 1.0, 0.0, sd.gws->p);
 }
-// dense m x r all-reduce of an m-side matrix with ld == m
-static void allreduce_mside(dlra_handle h, double* L, int r) { h->comm.allreduce_sum(L, h->m * (int64_t)r, h->cx.stream); }
 // p x q small matrix with ld W: stage densely, reduce, copy back
 static void allreduce_small(dlra_handle h, double* C, int p, int q) {
     if (h->comm.nranks <= 1) return;
     copy_mat(h->cx, p, q, C, h->W, false, h->T2, p);
-    h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx.stream);
+    h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx);
     copy_mat(h->cx, p, q, h->T2, p, false, C, h->W);
 }
 
@@ -369,9 +399,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     // K = U0*S0 (+ ΔA*V0);  L = V0*S0' (+ ΔA'*U0)   — one fused read of ΔA
     gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);
     if (sc.is_data) {
-        pass_KL(h, sc.d, r, h->V, m, h->U, n, K, n, L, m);
-        allreduce_mside(h, L, r);
-        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 1.0);
+        pass_KL(h, sc.d, r, h->V, m, h->U, n, K, n, L, m, h->V, m, h->S, W);   // L complete: all-reduced, + V0*S0'
     } else {
         gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 0.0);
         de_K_flow(h, K, r, h->V, sc.t, sc.dt);
@@ -381,15 +409,17 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     qr_mside(h, aux_side(h), L, r, nullptr);              // V1 = qr(L).Q
     gram_mside(h, aux_side(h), r, r, L, h->V, h->N);      // N = V1'*V0
     qr_nside(h, K, r, nullptr);                           // ... overlaps U1 = qr(K).Q
-    gram_nside(h, r, r, K, h->U, h->M);                   // M = U1'*U0
+    gram_nside_local(h, r, r, K, h->U, h->M);             // M = U1'*U0 (local rows; summed over ranks below)
     join_aux(h);
-    small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);   // T1 = M*S0
-    small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);   // Sh = M*S0*N'
     if (sc.is_data) {
-        pass_S(h, sc.d, r, r, K, n, L, m, h->T1, W);            // T1 = U1'*ΔA*V1 (local rows)
-        allreduce_small(h, h->T1, r, r);
-        copy_mat(cx, r, r, h->T1, W, false, h->Sh, W, 1.0, 1.0);
+        pass_S(h, sc.d, r, r, K, n, L, m, h->Rm, W);            // Rm = U1'*ΔA*V1 (local rows)
+        allreduce_pair(h, h->M, r, r, h->Rm, r, r);             // M and the core increment share one collective
+        small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);   // T1 = M*S0
+        small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);   // Sh = M*S0*N'
+        copy_mat(cx, r, r, h->Rm, W, false, h->Sh, W, 1.0, 1.0);
     } else {
+        small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);
+        small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);
         de_S_flow(h, h->Sh, r, r, K, L, +1.0, sc.t, sc.dt);
     }
     std::swap(h->U, h->UB);
@@ -412,7 +442,6 @@ static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
     if (sc.is_data) {
         // W = ΔA'*U1 ; S~ = R − W'*V0 ; L = V0*S~' + W        (U1'ΔA V0 == W'V0)
         pass_KL(h, sc.d, r, nullptr, 0, K, n, nullptr, 0, L, m);
-        allreduce_mside(h, L, r);
         gram_mside(h, main_side(h), r, r, L, h->V, h->T1);                                    // T1 = W'*V0
         copy_mat(cx, r, r, h->Rm, W, false, h->Sh, W);
         copy_mat(cx, r, r, h->T1, W, false, h->Sh, W, -1.0, 1.0);                             // Sh = R − W'V0
@@ -435,9 +464,7 @@ static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
     const int64_t n = h->n, m = h->m, W = h->W;
     double *K = h->UB, *L = h->VB;
     if (sc.is_data) {
-        pass_KL(h, sc.d, r, nullptr, 0, h->U, n, nullptr, 0, L, m);                           // L = ΔA'*U0
-        allreduce_mside(h, L, r);
-        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 1.0);             //   + V0*S0'
+        pass_KL(h, sc.d, r, nullptr, 0, h->U, n, nullptr, 0, L, m, h->V, m, h->S, W);         // L = ΔA'*U0 + V0*S0'
     } else {
         gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 0.0);
         de_L_flow(h, L, r, h->U, sc.t, sc.dt);
@@ -478,9 +505,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     double *Kh = h->UB, *Lh = h->VB;   // [K U0] -> Uhat ; [L V0] -> Vhat
     gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, Kh, n, 1.0, 0.0);
     if (sc.is_data) {
-        pass_KL(h, sc.d, r, h->V, m, h->U, n, Kh, n, Lh, m);
-        allreduce_mside(h, Lh, r);
-        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, Lh, m, 1.0, 1.0);
+        pass_KL(h, sc.d, r, h->V, m, h->U, n, Kh, n, Lh, m, h->V, m, h->S, W);
     } else {
         gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, Lh, m, 1.0, 0.0);
         de_K_flow(h, Kh, r, h->V, sc.t, sc.dt);
@@ -492,15 +517,17 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     qr_mside(h, aux_side(h), Lh, r2, nullptr);
     gram_mside(h, aux_side(h), r2, r, Lh, h->V, h->N);                   // N = Vhat'*V0
     qr_nside(h, Kh, r2, nullptr);
-    gram_nside(h, r2, r, Kh, h->U, h->M);                                // M = Uhat'*U0 (2r x r)
+    gram_nside_local(h, r2, r, Kh, h->U, h->M);                          // M = Uhat'*U0 (2r x r), local rows
     join_aux(h);
-    small_gemm(cx, r2, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);
-    small_gemm(cx, r2, r2, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);
     if (sc.is_data) {
-        pass_S(h, sc.d, r2, r2, Kh, n, Lh, m, h->T1, W);
-        allreduce_small(h, h->T1, r2, r2);
-        copy_mat(cx, r2, r2, h->T1, W, false, h->Sh, W, 1.0, 1.0);
+        pass_S(h, sc.d, r2, r2, Kh, n, Lh, m, h->Rm, W);
+        allreduce_pair(h, h->M, r2, r, h->Rm, r2, r2);
+        small_gemm(cx, r2, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);
+        small_gemm(cx, r2, r2, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);
+        copy_mat(cx, r2, r2, h->Rm, W, false, h->Sh, W, 1.0, 1.0);
     } else {
+        small_gemm(cx, r2, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);
+        small_gemm(cx, r2, r2, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);
         de_S_flow(h, h->Sh, r2, r2, Kh, Lh, +1.0, sc.t, sc.dt);
     }
     h->jws.ensure((int64_t)jacobi_ws_doubles(r2), cx.stream);
@@ -528,8 +555,7 @@ static void greedy_step(dlra_handle h, const Delta& x) {
     const int64_t n = h->n, m = h->m, W = h->W;
     double *XV = h->UB, *XU = h->VB;
     fill_mat(cx, n, r, XV, n, 0.0, 0.0);
-    pass_KL(h, x, r, h->V, m, h->U, n, XV, n, XU, m);        // XV = X*V ; XU = X'*U
-    allreduce_mside(h, XU, r);
+    pass_KL(h, x, r, h->V, m, h->U, n, XV, n, XU, m);        // XV = X*V ; XU = X'*U (all-reduced)
     fork_aux(h);
     qr_mside(h, aux_side(h), XU, r, nullptr);
     qr_nside(h, XV, r, nullptr);
@@ -646,7 +672,7 @@ extern "C" int dlra_reconstruct_error(dlra_handle h, const double* Yref, int64_t
     DLRA_CUDA(cudaGetLastError());
     sum_pairs_kernel<<<1, 1024, 0, h->cx.stream>>>(nblocks, h->gws.p, h->scal_dev);
     h->cx.launches++;
-    h->comm.allreduce_sum(h->scal_dev, 2, h->cx.stream);
+    h->comm.allreduce_sum(h->scal_dev, 2, h->cx);
     double out[2];
     DLRA_CUDA(cudaMemcpyAsync(out, h->scal_dev, 16, cudaMemcpyDeviceToHost, h->cx.stream));
     DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));

@@ -70,7 +70,7 @@ struct dlra_engine {
     // factors (ld: U -> n, V -> m, small -> W)
     double *U = nullptr, *UB = nullptr, *V = nullptr, *VB = nullptr, *S = nullptr;
     // small matrices, each W x W, ld = W
-    double *M = nullptr, *N = nullptr, *Sh = nullptr, *T1 = nullptr, *T2 = nullptr, *Rm = nullptr, *Pm = nullptr, *Qm = nullptr, *sig = nullptr;
+    double *M = nullptr, *N = nullptr, *Sh = nullptr, *T1 = nullptr, *T2 = nullptr, *Rm = nullptr, *Pm = nullptr, *Qm = nullptr, *sig = nullptr, *stg = nullptr;
     double* small_block = nullptr;
     int* r_new_dev = nullptr;
     int* r_new_host = nullptr;  // pinned, mapped

@@ -390,6 +390,89 @@ inline void launch_pass_rt(dlra_engine* e, const Delta& d, int rc, const double*
 #undef DLRA_PASS_CASE
 }
 
+// Fused tail of the L-use: fixed-order sum of the per-CTA partials, cross-rank sum over NVLink peer memory (P2P transport,
+// row-sharded runs) and the initial term  L += Vi·Siᵀ  (the reference's `mul!(VS, V, S')` before the L-step,
+// unconventional.jl:145) in ONE launch.  XR: post the local sum to the exchange buffer, the last CTA raises this rank's
+// sequence flag in every peer, then all CTAs wait for the peers' flags and add the peers' slices in rank order.
+template <bool XR>
+__global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int nparts, const double* __restrict__ part, int64_t ldlp,
+                                                         int64_t part_stride, const double* __restrict__ Vi, int64_t ldvi,
+                                                         const double* __restrict__ Si, int64_t ldsi, int rk, double* __restrict__ L,
+                                                         int64_t ldl, P2PView v, unsigned int* ticket) {
+    extern __shared__ double Ss[];   // [rc][rk]
+    if (Vi) {
+        for (int e = threadIdx.x; e < rc * rk; e += blockDim.x) Ss[e] = Si[(e / rk) + (int64_t)(e % rk) * ldsi];
+    }
+    __syncthreads();
+    const int64_t total = m * rc;
+    const int64_t gstride = (int64_t)gridDim.x * blockDim.x;
+    auto init_term = [&](int64_t j, int c) {
+        double t = 0.0;
+        if (Vi) {
+            const double* sr = Ss + c * rk;
+            for (int k = 0; k < rk; ++k) t = fma(Vi[j + (int64_t)k * ldvi], sr[k], t);
+        }
+        return t;
+    };
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gstride) {
+        const int64_t j = e % m;
+        const int c = (int)(e / m);
+        double s = 0.0;
+        const double* pp = part + j + (int64_t)c * ldlp;
+#pragma unroll 8
+        for (int p = 0; p < nparts; ++p) s += pp[(int64_t)p * part_stride];
+        if (XR) v.data_local[e] = s;
+        else L[j + (int64_t)c * ldl] = s + init_term(j, c);
+    }
+    if (!XR) return;
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < v.nranks) st_release_sys(v.flags_peer[threadIdx.x] + (size_t)v.rank * P2P_FLAG_STRIDE, v.seq);
+        if (threadIdx.x == 0) *ticket = 0;
+    }
+    p2p_wait_all(v);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gstride) {
+        const int64_t j = e % m;
+        const int c = (int)(e / m);
+        double s = 0.0;
+        for (int g = 0; g < v.nranks; ++g) s += ld_relaxed_sys(v.data_peer[g] + e);
+        L[j + (int64_t)c * ldl] = s + init_term(j, c);
+    }
+}
+
+// Lout chunk (m x rc) = Σ_parts (+ Σ_ranks) + Vi·Siᵀ ; picks the fused kernel when it can (single GPU or P2P transport)
+inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, int64_t ldlp, int64_t part_stride, const double* Vi,
+                       int64_t ldvi, const double* Si, int64_t ldsi, int rk, double* L, int64_t ldl) {
+    Ctx& cx = e->cx;
+    Comm& cm = e->comm;
+    const int64_t total = e->m * (int64_t)rc;
+    // the cross-rank variant spins on peer flags, so its whole grid must be co-resident (256 threads, <= 16 KB smem: >= 4 CTAs/SM)
+    const bool xr = cm.nranks > 1 && cm.p2p;
+    const int grid = (int)std::min<int64_t>(cdiv(total, 256), xr ? 4 * (int64_t)cx.num_sms : ((int64_t)1 << 30));
+    const size_t smem = Vi ? (size_t)rc * rk * sizeof(double) : 0;
+    if (cm.nranks <= 1) {
+        l_finalize_kernel<false><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, Vi, ldvi, Si, ldsi, rk, L, ldl, P2PView{}, nullptr);
+        cx.launches++;
+    } else if (cm.p2p) {
+        DLRA_REQUIRE((size_t)total * 8 <= cm.xdata_bytes, "P2P exchange region too small for an L chunk");
+        P2PView v = cm.next_view();
+        l_finalize_kernel<true><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, Vi, ldvi, Si, ldsi, rk, L, ldl, v, cm.ticket);
+        cx.launches++;
+    } else {
+        // NCCL transport: local reduction, library all-reduce of the dense chunk (ldl == m), then the initial term
+        reduce_parts(cx, (int)e->m, rc, nparts, part, ldlp, part_stride, L, ldl, 1.0, 0.0);
+        if (ldl == e->m) cm.allreduce_sum(L, total, cx);
+        else for (int c = 0; c < rc; ++c) cm.allreduce_sum(L + (int64_t)c * ldl, e->m, cx);
+        if (Vi) gemm_nn(cx, e->m, rk, rc, Vi, ldvi, nullptr, 0, Si, ldsi, true, L, ldl, 1.0, 1.0);
+    }
+    DLRA_CUDA(cudaGetLastError());
+}
+
 // K-only launches also exist with 32 factor columns per chunk (K accumulators + V fragments still fit the register file):
 // at r = 32 a K-only pass is HBM-bound again, so one sweep instead of two halves its time.
 inline void launch_pass_k32(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, double* K, int64_t ldk, int nsub,
@@ -399,8 +482,10 @@ inline void launch_pass_k32(dlra_engine* e, const Delta& d, int rc, const double
 }
 
 // K (n x r) += ΔA·Vf and/or Lout (m x r, ldl) = ΔAᵀ·Uf, r processed in chunks of 16 (8 for a narrow tail)
+// Lout is COMPLETE on return: summed over this rank's panels, over the ranks of a row-sharded run, plus Vi·Siᵀ if given.
 inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
-                        double* K, int64_t ldk, double* Lout, int64_t ldl) {
+                        double* K, int64_t ldk, double* Lout, int64_t ldl, const double* Vi = nullptr, int64_t ldvi = 0,
+                        const double* Si = nullptr, int64_t ldsi = 0) {
     // factor operands must satisfy the TMA alignment rules too; otherwise stage them through aligned scratch
     DLRA_REQUIRE((!K || tma_ok(Vf, ldv)) && (!Lout || tma_ok(Uf, ldu)), "factor buffers must be 16-byte aligned with even ld");
     const int nsub = choose_nsub(e->n, e->cx.num_sms);
@@ -422,10 +507,10 @@ inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf,
         const double* Uc = Uf ? Uf + (int64_t)c0 * ldu : nullptr;
         if (rc <= 8) {
             launch_pass_rt<8>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
-            if (Lout) reduce_parts(e->cx, (int)e->m, rc, nparts, Lp, ldlp, ldlp * 8, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
+            if (Lout) l_finalize(e, rc, nparts, Lp, ldlp, ldlp * 8, Vi, ldvi, Si ? Si + c0 : nullptr, ldsi, r, Lout + (int64_t)c0 * ldl, ldl);
         } else {
             launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
-            if (Lout) reduce_parts(e->cx, (int)e->m, rc, nparts, Lp, ldlp, ldlp * 16, Lout + (int64_t)c0 * ldl, ldl, 1.0, 0.0);
+            if (Lout) l_finalize(e, rc, nparts, Lp, ldlp, ldlp * 16, Vi, ldvi, Si ? Si + c0 : nullptr, ldsi, r, Lout + (int64_t)c0 * ldl, ldl);
         }
         c0 += rc;
     }

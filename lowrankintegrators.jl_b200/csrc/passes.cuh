@@ -13,12 +13,14 @@ namespace dlra {
 
 inline double delta_bytes(const dlra_engine* e, const Delta& d) { return (double)e->n * (double)e->m * 8.0 * (d.Aprev ? 2.0 : 1.0); }
 
-// K (n x r, ldk) += ΔA·Vf  if K != nullptr ;  Lout (m x r, ldl) = ΔAᵀ·Uf (this rank's rows only) if Lout != nullptr
+// K (n x r, ldk) += ΔA·Vf  if K != nullptr (this rank's rows);
+// Lout (m x r, ldl) = Σ_ranks ΔAᵀ·Uf + Vi·Siᵀ  if Lout != nullptr  (complete: all-reduced over row shards, initial term added)
 inline void pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
-                    double* K, int64_t ldk, double* Lout, int64_t ldl) {
+                    double* K, int64_t ldk, double* Lout, int64_t ldl, const double* Vi = nullptr, int64_t ldvi = 0,
+                    const double* Si = nullptr, int64_t ldsi = 0) {
     Ctx& cx = e->cx;
     if (!(e->flags & DLRA_FORCE_GENERIC) && tma_pass_supported(e->n, e->m, d)) {
-        tma_pass_KL(e, d, r, Vf, ldv, Uf, ldu, K, ldk, Lout, ldl);   // timed per kernel launch inside
+        tma_pass_KL(e, d, r, Vf, ldv, Uf, ldu, K, ldk, Lout, ldl, Vi, ldvi, Si, ldsi);   // timed per kernel launch inside
         return;
     }
     if (K) {
@@ -31,6 +33,9 @@ inline void pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int
         pass_timer_begin(e, delta_bytes(e, d), 2, 2.0 * (double)e->n * (double)e->m * r);
         gemm_tn(cx, e->n, (int)e->m, r, d.A, d.lda, d.Aprev, d.ldap, Uf, ldu, Lout, ldl, 1.0, 0.0, e->gws.p);
         pass_timer_end(e);
+        if (ldl == e->m) e->comm.allreduce_sum(Lout, e->m * (int64_t)r, cx);
+        else for (int c = 0; c < r; ++c) e->comm.allreduce_sum(Lout + (int64_t)c * ldl, e->m, cx);
+        if (Vi) gemm_nn(cx, e->m, r, r, Vi, ldvi, nullptr, 0, Si, ldsi, true, Lout, ldl, 1.0, 1.0);
     }
 }
 

@@ -392,7 +392,7 @@ inline void tsqr(Ctx& cx, Comm& comm, int64_t rows, int C, const double* A, int6
         double* stacked = gathered + (int64_t)G * CP * CP;      // (G*CP) x CP, ld = G*CP
         double* Qg = stacked + (int64_t)G * CP * CP;            // (G*CP) x CP
         double* ws2 = Qg + (int64_t)G * CP * CP;
-        comm.allgather(Rloc, gathered, (int64_t)CP * CP, cx.stream);
+        comm.allgather(Rloc, gathered, (int64_t)CP * CP, cx);
         for (int g = 0; g < G; ++g) copy_mat(cx, CP, CP, gathered + (int64_t)g * CP * CP, CP, false, stacked + (int64_t)g * CP, (int64_t)G * CP);
         DLRA_REQUIRE((int64_t)G * CP <= TSQR_BR, "too many ranks for the single-CTA R reduction");
         double* Rg = tsqr_local(cx, (int64_t)G * CP, CP, stacked, (int64_t)G * CP, Qg, (int64_t)G * CP, ws2);
@@ -431,12 +431,12 @@ inline void thin_qr(Ctx& cx, Comm& comm, int64_t rows, int C, double* A, int64_t
         }
         // first pass: W1 = Qprev' * Ap ; Ap -= Qprev * W1 ; Ap = Qhat * R1
         gemm_tn(cx, rows, c0, cb, Q, ldq, nullptr, 0, Ap, lda, W1, c0, 1.0, 0.0, gws);
-        comm.allreduce_sum(W1, (int64_t)c0 * cb, cx.stream);
+        comm.allreduce_sum(W1, (int64_t)c0 * cb, cx);
         gemm_nn(cx, rows, c0, cb, Q, ldq, nullptr, 0, W1, c0, false, Ap, lda, -1.0, 1.0);
         tsqr(cx, comm, rows, cb, Ap, lda, Qp, ldq, R1, LR, tws);
         // second pass on the orthonormal block: W2 = Qprev' * Qhat ; Qhat -= Qprev * W2 ; Qhat = Qp * R2
         gemm_tn(cx, rows, c0, cb, Q, ldq, nullptr, 0, Qp, ldq, W2, c0, 1.0, 0.0, gws);
-        comm.allreduce_sum(W2, (int64_t)c0 * cb, cx.stream);
+        comm.allreduce_sum(W2, (int64_t)c0 * cb, cx);
         gemm_nn(cx, rows, c0, cb, Q, ldq, nullptr, 0, W2, c0, false, Qp, ldq, -1.0, 1.0);
         tsqr(cx, comm, rows, cb, Qp, ldq, Qp, ldq, R ? R2 : nullptr, LR, tws);
         if (R) {

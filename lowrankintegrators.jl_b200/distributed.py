@@ -24,3 +24,21 @@ def comm_from_torch():
 
 def env_rank():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def attach_engine(engine, transport=None):
+    """Join `engine` to the initialised torch.distributed group.  transport: "nccl" (default; measured ~2 % faster per step
+    at 2 and 8 GPUs) or "p2p" (CUDA-IPC peer memory over NVLink: the L tail becomes ONE kernel that sums the per-CTA
+    partials, the peers' contributions and the initial term); DLRA_COMM overrides.  A no-op for world size 1."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
+        return None
+    transport = os.environ.get("DLRA_COMM", transport or "nccl")
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if transport == "p2p":
+        handles = [None] * world
+        dist.all_gather_object(handles, engine.p2p_export())
+        engine.p2p_import(world, rank, handles)
+    else:
+        engine.comm_init(*comm_from_torch())
+    return transport

@@ -85,6 +85,17 @@ class Engine:
         buf = C.create_string_buffer(unique_id, 128)
         self._ck(self.lib.dlra_comm_init(self.h, nranks, rank, buf))
 
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._ck(self.lib.dlra_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_import(self, nranks, rank, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * nranks
+        buf = C.create_string_buffer(blob, len(blob))
+        self._ck(self.lib.dlra_p2p_import(self.h, nranks, rank, buf))
+
     @staticmethod
     def nccl_unique_id() -> bytes:
         lib = L.load()

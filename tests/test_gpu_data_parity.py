@@ -70,7 +70,7 @@ def test_step_parity_small_generic(lri, name, device_data):
 
 
 @pytest.mark.parametrize("name", ["bug", "ksl_primal", "ksl_dual", "rabug", "greedy"])
-@pytest.mark.parametrize("shape", [(1024, 512, 16), (2048, 384, 8), (4096, 256, 32), (1000, 130, 5)])
+@pytest.mark.parametrize("shape", [(1024, 512, 16), (2048, 384, 8), (4096, 256, 32), (1000, 130, 5), (2048, 256, 24), (1536, 320, 40)])
 def test_step_parity_fast_path(lri, name, shape):
     n, m, r = shape
     A = lowrank_stream(n, m, 2 * r if name != "rabug" else r + r // 2, seed=7, eps=0.0 if name == "rabug" else 1e-4)

@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_row_sharded_steps_match_oracle():
+@pytest.mark.parametrize("transport", ["nccl", "p2p"])
+def test_row_sharded_steps_match_oracle(transport):
     import torch
     ngpu = torch.cuda.device_count()
     if ngpu < 2:
@@ -17,5 +18,5 @@ def test_row_sharded_steps_match_oracle():
     world = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29531", os.path.join(ROOT, "tests", "multi_gpu_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, DLRA_COMM=transport))
     assert "MULTI_GPU_OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
