@@ -143,7 +143,7 @@ inline void reduce_parts(Ctx& cx, int p, int q, int nchunks, const double* part,
 // tiles are summed in shared memory, every CTA stores one partial and the LAST CTA to finish (ticket counter) adds the
 // partials in fixed order — deterministic without a second launch.
 // ------------------------------------------------------------------------------------------------
-constexpr int GRAM_ROWS_PER_CTA = 1024;
+constexpr int GRAM_ROWS_PER_CTA = 512;
 __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
                                                         const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
                                                         double alpha, double beta, double* __restrict__ part, unsigned int* __restrict__ counters) {
@@ -157,6 +157,7 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q,
     const bool b_ok[2] = {b0 + g < q, b0 + 8 + g < q};
     const double* Ap[2] = {A + (int64_t)(a0 + g) * lda, A + (int64_t)(a0 + 8 + g) * lda};
     const double* Bp[2] = {B + (int64_t)(b0 + g) * ldb, B + (int64_t)(b0 + 8 + g) * ldb};
+#pragma unroll 4
     for (int64_t row = r0 + 4 * warp; row < r1; row += 32) {
         const int64_t i = row + k;
         const bool ok = i < r1;
