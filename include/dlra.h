@@ -113,7 +113,10 @@ int dlra_factor_ptrs(dlra_handle h, const double** U, int64_t* ldu, const double
  * BORROW the pointer: it must stay valid and unmodified until the step after the next push has run. */
 int dlra_data_init(dlra_handle h, const double* A0, int64_t ld);
 int dlra_data_init_host(dlra_handle h, const double* A0, int64_t ld);
-/* update_data!(ycurr, y, t, dt) for the NEXT step; kind = DLRA_DATA_SNAPSHOT | DLRA_DATA_DELTA */
+/* update_data!(ycurr, y, t, dt) for the NEXT step; kind = DLRA_DATA_SNAPSHOT | DLRA_DATA_DELTA.
+ * A SECOND push before the step is a one-snapshot lookahead (the data of the step after next): with it dlra_step_bug
+ * forms the next step's K/L contractions in the same sweep as this step's core pass (each snapshot is then read three
+ * times instead of four); results are identical.  The lookahead snapshot becomes the pushed data of the next step. */
 int dlra_data_push(dlra_handle h, const double* A, int64_t ld, int kind);
 int dlra_data_push_host(dlra_handle h, const double* A, int64_t ld, int kind);
 
@@ -160,8 +163,9 @@ int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass_launches, 
                double* pass_bytes_total, int reset);
 int dlra_set_profiling(dlra_handle h, int time_passes);
 /* per-kind breakdown of the timed contraction launches since the last reset:
- * index 0 = fused K+L pass, 1 = K-only pass (also the first half of the S pass), 2 = L-only pass */
-int dlra_pass_breakdown(dlra_handle h, int64_t launches[3], double ms[3], double bytes[3], double flops[3]);
+ * index 0 = fused K+L pass, 1 = K-only pass (also the first half of the S pass), 2 = L-only pass,
+ * 3 = software-pipelined BUG pass (core of step k + K/L of step k+1 in one sweep over three snapshots) */
+int dlra_pass_breakdown(dlra_handle h, int64_t launches[4], double ms[4], double bytes[4], double flops[4]);
 /* CUDA events on the ENGINE's stream (torch.cuda.Event only sees torch's streams): slots 0..7 */
 int dlra_event_record(dlra_handle h, int slot);
 int dlra_event_elapsed_ms(dlra_handle h, int slot_begin, int slot_end, double* ms); /* synchronises on slot_end */

@@ -120,6 +120,7 @@ class DLRSolution:
 class DLRIntegrator:
     def __init__(self, engine, t, dt, sol, alg, probType, prob, save_everystep):
         self.cache = engine  # the reference's alg cache == the engine's device workspaces
+        self._pushed = 0     # snapshots already handed to the engine beyond the current time (0, 1 or 2)
         self.t, self.dt, self.sol, self.alg, self.probType, self.iter = t, dt, sol, alg, probType, 0
         self.prob = prob
         self.save_everystep = save_everystep
@@ -219,7 +220,14 @@ def _fetch(y, t, dt):
     return y[t + dt - 1]
 
 
-def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False) -> DLRIntegrator:
+def _has_snapshot(y, tspan, t, ahead):
+    """Is y(t + ahead) / y[t + ahead] inside the problem's time span?"""
+    if callable(y):
+        return (t + ahead) <= tspan[1] * (1 + 1e-12) + 1e-300
+    return isinstance(t, (int, np.integer)) and (t + ahead - 1) < len(y) and (t + ahead) <= tspan[1]
+
+
+def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False, lookahead=True) -> DLRIntegrator:
     """init(prob, alg, dt): projector_splitting.jl:107-115, unconventional.jl:109-119,
     rank_adaptive_unconventional.jl:94-104, greedy_integrator.jl:49-59.  `comm` = "torch" (use the initialised torch.distributed group to distribute
     a fresh ncclUniqueId) or (nranks, rank, unique_id) row-shards the problem: every rank passes ITS row block of u0.U
@@ -253,7 +261,9 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
             eng.set_substepper(flow, _ODE[sub.kind], sub.nsub, sub.abstol, sub.reltol)
     sol = init_sol(dt, t0, tf, u0)
     sol.Y[0] = u0.copy() if hasattr(u0, "copy") else u0
-    return DLRIntegrator(eng, t0, dt, sol, alg, type(prob), prob, save_everystep)
+    integ = DLRIntegrator(eng, t0, dt, sol, alg, type(prob), prob, save_everystep)
+    integ.lookahead = bool(lookahead)
+    return integ
 
 
 def step(integ: DLRIntegrator, alg=None, dt=None):
@@ -279,7 +289,15 @@ def step(integ: DLRIntegrator, alg=None, dt=None):
             eng.step_ksl(L.KSL_PRIMAL if isinstance(alg.order, PrimalLieTrotter) else L.KSL_DUAL, t, dt)
     elif isinstance(alg, UnconventionalAlgorithm):
         if is_data:
-            eng.data_push(_fetch(y, t, dt))
+            # update_data! for this step, plus one snapshot of lookahead when the stream has it: the engine then forms the
+            # next step's K/L contractions in the same sweep as this step's core pass (identical results, 3/4 of the HBM reads)
+            if integ._pushed == 0:
+                eng.data_push(_fetch(y, t, dt))
+                integ._pushed = 1
+            if integ._pushed == 1 and integ.lookahead and _has_snapshot(y, integ.prob.tspan, t, 2 * dt):
+                eng.data_push(_fetch(y, t, 2 * dt))
+                integ._pushed = 2
+            integ._pushed -= 1
         eng.step_bug(t, dt)
     elif isinstance(alg, RankAdaptiveUnconventionalAlgorithm):
         if is_data:

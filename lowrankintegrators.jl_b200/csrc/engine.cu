@@ -76,7 +76,7 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         DLRA_CUDA(cudaMalloc(&e->r_new_dev, sizeof(int)));
         DLRA_CUDA(cudaHostAlloc(&e->r_new_host, sizeof(int), cudaHostAllocDefault));
         *e->r_new_host = r0;
-        for (int i = 0; i < 3; ++i) {
+        for (int i = 0; i < dlra_engine::NOWN; ++i) {
             DLRA_CUDA(cudaEventCreateWithFlags(&e->own_free[i], cudaEventDisableTiming));
             DLRA_CUDA(cudaEventCreateWithFlags(&e->own_ready[i], cudaEventDisableTiming));
         }
@@ -101,7 +101,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     h->comm.destroy();
     cudaFree(h->U); cudaFree(h->UB); cudaFree(h->V); cudaFree(h->VB); cudaFree(h->small_block);
     cudaFree(h->r_new_dev); cudaFreeHost(h->r_new_host); cudaFree(h->cx.counters);
-    for (int i = 0; i < 3; ++i) { if (h->own[i]) cudaFree(h->own[i]); cudaEventDestroy(h->own_free[i]); cudaEventDestroy(h->own_ready[i]); }
+    for (int i = 0; i < dlra_engine::NOWN; ++i) { if (h->own[i]) cudaFree(h->own[i]); cudaEventDestroy(h->own_free[i]); cudaEventDestroy(h->own_ready[i]); }
     h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release();
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int i = 0; i < 8; ++i) if (h->user_events[i]) cudaEventDestroy(h->user_events[i]);
@@ -170,6 +170,7 @@ static void set_factors_impl(dlra_handle h, const double* U, int64_t ldu, const 
     DLRA_CUDA(cudaMemcpy2DAsync(h->V, h->m * 8, V, ldv * 8, h->m * 8, r, kind, s));
     DLRA_CUDA(cudaMemcpy2DAsync(h->S, (size_t)h->W * 8, S, lds * 8, (size_t)r * 8, r, kind, s));
     h->r = r;
+    h->kl_ready = false;   // a precomputed K/L pass belongs to the factors it was formed with
     if (kind == cudaMemcpyHostToDevice) DLRA_CUDA(cudaStreamSynchronize(s));
 }
 extern "C" int dlra_set_factors_host(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds, const double* V,
@@ -224,14 +225,14 @@ extern "C" int dlra_factor_ptrs(dlra_handle h, const double** U, int64_t* ldu, c
 // data feed
 // ---------------------------------------------------------------------------------------------------
 static int own_slot_for_copy(dlra_handle h) {
-    // rotate over three engine-owned n x m buffers so that an H2D copy for step k+1 overlaps step k
+    // rotate over four engine-owned n x m buffers (prev, cur, lookahead + one in flight) so that H2D copies overlap the steps
     int slot = -1;
-    for (int tries = 0; tries < 3; ++tries) {
-        int cand = (h->own_next + tries) % 3;
-        if (cand != h->cur_own && cand != h->prev_own) { slot = cand; break; }
+    for (int tries = 0; tries < dlra_engine::NOWN; ++tries) {
+        int cand = (h->own_next + tries) % dlra_engine::NOWN;
+        if (cand != h->cur_own && cand != h->prev_own && cand != h->nxt_own) { slot = cand; break; }
     }
     DLRA_REQUIRE(slot >= 0, "no free snapshot buffer");
-    h->own_next = (slot + 1) % 3;
+    h->own_next = (slot + 1) % dlra_engine::NOWN;
     if (!h->own[slot]) {
         cudaError_t er = cudaMalloc(&h->own[slot], (size_t)h->n * h->m * 8);
         if (er != cudaSuccess) throw CudaError(5, std::string("cudaMalloc(snapshot buffer) failed: ") + cudaGetErrorString(er));
@@ -249,12 +250,13 @@ extern "C" int dlra_data_init(dlra_handle h, const double* A0, int64_t ld) {
     DLRA_API_BEGIN(h)
     DLRA_REQUIRE(A0 && ld >= h->n, "bad snapshot pointer / leading dimension");
     h->prev = A0; h->ldprev = ld; h->prev_own = -1; h->have_cur = false; h->cur_own = -1;
+    h->have_nxt = false; h->nxt_own = -1; h->kl_ready = false;
     DLRA_API_END(h)
 }
 extern "C" int dlra_data_init_host(dlra_handle h, const double* A0, int64_t ld) {
     DLRA_API_BEGIN(h)
     DLRA_REQUIRE(A0 && ld >= h->n, "bad snapshot pointer / leading dimension");
-    h->prev_own = -1; h->cur_own = -1; h->have_cur = false;
+    h->prev_own = -1; h->cur_own = -1; h->have_cur = false; h->have_nxt = false; h->nxt_own = -1; h->kl_ready = false;
     int slot = own_slot_for_copy(h);
     copy_host_snapshot(h, slot, A0, ld);
     DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->own_ready[slot], 0));
@@ -265,16 +267,23 @@ extern "C" int dlra_data_push(dlra_handle h, const double* A, int64_t ld, int ki
     DLRA_API_BEGIN(h)
     DLRA_REQUIRE(A && ld >= h->n, "bad snapshot pointer / leading dimension");
     DLRA_REQUIRE(kind == DLRA_DATA_SNAPSHOT || kind == DLRA_DATA_DELTA, "bad data kind");
-    h->cur = A; h->ldcur = ld; h->cur_kind = kind; h->have_cur = true; h->cur_own = -1;
+    if (h->have_cur) {   // second push before the step: one-snapshot lookahead (enables the software-pipelined BUG pass)
+        DLRA_REQUIRE(!h->have_nxt, "at most one snapshot of lookahead can be pushed");
+        h->nxt = A; h->ldnxt = ld; h->nxt_kind = kind; h->have_nxt = true; h->nxt_own = -1;
+    } else {
+        h->cur = A; h->ldcur = ld; h->cur_kind = kind; h->have_cur = true; h->cur_own = -1;
+    }
     DLRA_API_END(h)
 }
 extern "C" int dlra_data_push_host(dlra_handle h, const double* A, int64_t ld, int kind) {
     DLRA_API_BEGIN(h)
     DLRA_REQUIRE(A && ld >= h->n, "bad snapshot pointer / leading dimension");
     DLRA_REQUIRE(kind == DLRA_DATA_SNAPSHOT || kind == DLRA_DATA_DELTA, "bad data kind");
+    DLRA_REQUIRE(!(h->have_cur && h->have_nxt), "at most one snapshot of lookahead can be pushed");
     int slot = own_slot_for_copy(h);
     copy_host_snapshot(h, slot, A, ld);
-    h->cur = h->own[slot]; h->ldcur = h->n; h->cur_kind = kind; h->have_cur = true; h->cur_own = slot;
+    if (h->have_cur) { h->nxt = h->own[slot]; h->ldnxt = h->n; h->nxt_kind = kind; h->have_nxt = true; h->nxt_own = slot; }
+    else { h->cur = h->own[slot]; h->ldcur = h->n; h->cur_kind = kind; h->have_cur = true; h->cur_own = slot; }
     DLRA_API_END(h)
 }
 
@@ -301,6 +310,10 @@ static void end_data_step(dlra_handle h) {
         DLRA_CUDA(cudaEventRecord(h->own_free[h->cur_own], h->cx.stream));
     }
     h->have_cur = false; h->cur_own = -1; h->cur = nullptr;
+    if (h->have_nxt) {   // the lookahead snapshot becomes the pushed data of the next step
+        h->cur = h->nxt; h->ldcur = h->ldnxt; h->cur_kind = h->nxt_kind; h->cur_own = h->nxt_own; h->have_cur = true;
+        h->have_nxt = false; h->nxt = nullptr; h->nxt_own = -1;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -397,8 +410,16 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     const int64_t n = h->n, m = h->m, W = h->W;
     double *K = h->UB, *L = h->VB;
     // K = U0*S0 (+ ΔA*V0);  L = V0*S0' (+ ΔA'*U0)   — one fused read of ΔA
-    gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);
-    if (sc.is_data) {
+    const bool pre = sc.is_data && h->kl_ready && h->kl_rank == r;   // formed by the previous step's pipelined pass
+    h->kl_ready = false;
+    if (pre) {
+        gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 1.0);                        // K = ΔA*V0 + U0*S0
+        l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, h->kl_ldlp * 16, h->V, m, h->S, W, r, L, m);  // L = ΔA'*U0 + V0*S0'
+    } else {
+        gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);
+    }
+    if (pre) {
+    } else if (sc.is_data) {
         pass_KL(h, sc.d, r, h->V, m, h->U, n, K, n, L, m, h->V, m, h->S, W);   // L complete: all-reduced, + V0*S0'
     } else {
         gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, L, m, 1.0, 0.0);
@@ -412,7 +433,25 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     gram_nside_local(h, r, r, K, h->U, h->M);             // M = U1'*U0 (local rows; summed over ranks below)
     join_aux(h);
     if (sc.is_data) {
-        pass_S(h, sc.d, r, r, K, n, L, m, h->Rm, W);            // Rm = U1'*ΔA*V1 (local rows)
+        const bool pipe = !(h->flags & DLRA_FORCE_GENERIC) && h->have_nxt && h->nxt_kind == DLRA_DATA_SNAPSHOT && sc.d.Aprev != nullptr &&
+                          r <= 16 && tma_pass_supported(n, m, sc.d) && tma_ok(h->nxt, h->ldnxt);
+        if (pipe) {
+            // one sweep over A(t), A(t+dt), A(t+2dt): W = ΔA_k*V1 (this step's core) and ΔA_{k+1}*V1, ΔA_{k+1}'*U1 (next step)
+            if (h->nxt_own >= 0) DLRA_CUDA(cudaStreamWaitEvent(cx.stream, h->own_ready[h->nxt_own], 0));
+            const int nsub = choose_nsub(n, cx.num_sms);
+            const int npanels = (int)cdiv(cdiv(n, PT_SI), nsub);
+            const int nparts = std::min(npanels, cx.num_sms);
+            const int64_t ldlp = round_up(m, 2);
+            h->part.ensure((int64_t)nparts * ldlp * 16, cx.stream);
+            h->nscr.ensure(n * (int64_t)r, cx.stream);
+            tri_pass_launch(h, h->nxt, h->ldnxt, sc.d.A, sc.d.lda, sc.d.Aprev, sc.d.ldap, r, L, m, K, n, h->nscr.p, n,
+                            h->U /* old U0 buffer: the next step's K */, n, h->part.p, ldlp, nsub, npanels);
+            h->gws.ensure(gemm_tn_ws(cx, n, r, r), cx.stream);
+            gemm_tn(cx, n, r, r, K, n, nullptr, 0, h->nscr.p, n, h->Rm, W, 1.0, 0.0, h->gws.p);   // Rm = U1'*W (local rows)
+            h->kl_ready = true; h->kl_nparts = nparts; h->kl_ldlp = ldlp; h->kl_rank = r;
+        } else {
+            pass_S(h, sc.d, r, r, K, n, L, m, h->Rm, W);        // Rm = U1'*ΔA*V1 (local rows)
+        }
         allreduce_pair(h, h->M, r, r, h->Rm, r, r);             // M and the core increment share one collective
         small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);   // T1 = M*S0
         small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);   // Sh = M*S0*N'
@@ -432,6 +471,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
 // ---------------------------------------------------------------------------------------------------
 static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
     Ctx& cx = h->cx;
+    h->kl_ready = false;
     const int r = h->r;
     const int64_t n = h->n, m = h->m, W = h->W;
     double *K = h->UB, *L = h->VB;
@@ -460,6 +500,7 @@ static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
 
 static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
     Ctx& cx = h->cx;
+    h->kl_ready = false;
     const int r = h->r;
     const int64_t n = h->n, m = h->m, W = h->W;
     double *K = h->UB, *L = h->VB;
@@ -498,6 +539,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     const int r2 = 2 * r;
     const int64_t n = h->n, m = h->m, W = h->W;
     DLRA_REQUIRE(h->flags & DLRA_RANK_ADAPTIVE, "handle was created without DLRA_RANK_ADAPTIVE");
+    h->kl_ready = false;
     DLRA_REQUIRE(r2 <= W, "augmented basis exceeds workspace");
     DLRA_REQUIRE(r2 <= m, "augmented basis wider than the matrix");
     int rcap = (int)std::min<int64_t>(rcap64, (int64_t)h->rmax);
@@ -551,6 +593,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
 // ---------------------------------------------------------------------------------------------------
 static void greedy_step(dlra_handle h, const Delta& x) {
     Ctx& cx = h->cx;
+    h->kl_ready = false;
     const int r = h->r;
     const int64_t n = h->n, m = h->m, W = h->W;
     double *XV = h->UB, *XU = h->VB;
@@ -706,17 +749,17 @@ extern "C" int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass
     if (pass_bytes_total) *pass_bytes_total = h->pass_bytes;
     if (reset) {
         h->cx.launches = 0; h->ax.launches = 0; h->pass_launches = 0; h->pass_ms = 0.0; h->pass_bytes = 0.0;
-        for (int i = 0; i < 3; ++i) { h->kind_launches[i] = 0; h->kind_ms[i] = 0; h->kind_bytes[i] = 0; h->kind_flops[i] = 0; }
+        for (int i = 0; i < 4; ++i) { h->kind_launches[i] = 0; h->kind_ms[i] = 0; h->kind_bytes[i] = 0; h->kind_flops[i] = 0; }
     }
     DLRA_API_END(h)
 }
 
-extern "C" int dlra_pass_breakdown(dlra_handle h, int64_t launches[3], double ms[3], double bytes[3], double flops[3]) {
+extern "C" int dlra_pass_breakdown(dlra_handle h, int64_t launches[4], double ms[4], double bytes[4], double flops[4]) {
     DLRA_API_BEGIN(h)
     int64_t a, b; double c, d;
     int rc = dlra_stats(h, &a, &b, &c, &d, 0);   // folds pending events into the per-kind sums
     DLRA_REQUIRE(rc == DLRA_OK, "stats failed");
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < 4; ++i) {
         if (launches) launches[i] = h->kind_launches[i];
         if (ms) ms[i] = h->kind_ms[i];
         if (bytes) bytes[i] = h->kind_bytes[i];

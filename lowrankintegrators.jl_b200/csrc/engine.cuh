@@ -81,10 +81,14 @@ struct dlra_engine {
     // data feed
     const double* prev = nullptr; int64_t ldprev = 0;
     const double* cur = nullptr; int64_t ldcur = 0; int cur_kind = 0; bool have_cur = false;
-    double* own[3] = {nullptr, nullptr, nullptr};
-    cudaEvent_t own_free[3] = {nullptr, nullptr, nullptr};   // recorded on the compute stream when a step stops reading own[i]
-    cudaEvent_t own_ready[3] = {nullptr, nullptr, nullptr};  // recorded on the copy stream when the H2D copy landed
-    int own_next = 0; int cur_own = -1; int prev_own = -1;
+    const double* nxt = nullptr; int64_t ldnxt = 0; int nxt_kind = 0; bool have_nxt = false;   // one-snapshot lookahead
+    static constexpr int NOWN = 4;
+    double* own[NOWN] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t own_free[NOWN] = {nullptr, nullptr, nullptr, nullptr};   // recorded on the compute stream when a step stops reading own[i]
+    cudaEvent_t own_ready[NOWN] = {nullptr, nullptr, nullptr, nullptr};  // recorded on the copy stream when the H2D copy landed
+    int own_next = 0; int cur_own = -1; int prev_own = -1; int nxt_own = -1;
+    // software pipelining of the BUG step (pass_tri.cuh): ΔA·V0 already sits in UB and the per-CTA partials of ΔAᵀ·U0 in `part`
+    bool kl_ready = false; int kl_nparts = 0; int64_t kl_ldlp = 0; int kl_rank = 0;
 
     // DE problems
     dlra::RhsCfg rhs;
@@ -96,8 +100,8 @@ struct dlra_engine {
     std::vector<int> pass_event_kind;
     int64_t pass_launches = 0;
     double pass_bytes = 0.0, pass_ms = 0.0;
-    int64_t kind_launches[3] = {0, 0, 0};
-    double kind_ms[3] = {0, 0, 0}, kind_bytes[3] = {0, 0, 0}, kind_flops[3] = {0, 0, 0};
+    int64_t kind_launches[4] = {0, 0, 0, 0};
+    double kind_ms[4] = {0, 0, 0, 0}, kind_bytes[4] = {0, 0, 0, 0}, kind_flops[4] = {0, 0, 0, 0};
     cudaEvent_t user_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 

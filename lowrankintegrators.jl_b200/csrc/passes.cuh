@@ -8,6 +8,7 @@
 #pragma once
 #include "engine.cuh"
 #include "pass_tma.cuh"
+#include "pass_tri.cuh"
 
 namespace dlra {
 

@@ -153,8 +153,8 @@ class Engine:
         p, ld, host, keep = _ptr_ld(A)
         fn = self.lib.dlra_data_push_host if host else self.lib.dlra_data_push
         self._ck(fn(self.h, p, ld, kind))
-        # borrowed device pointers must outlive the step after next: keep the last three alive
-        self._keep["cur3"] = (self._keep.get("cur3", ()) + (keep,))[-3:]
+        # borrowed device pointers must outlive the step after next (plus one snapshot of lookahead): keep the last four alive
+        self._keep["cur3"] = (self._keep.get("cur3", ()) + (keep,))[-4:]
 
     # -- DE problems -------------------------------------------------------------------------------
     def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0):
@@ -238,10 +238,10 @@ class Engine:
         return {"kernel_launches": kl.value, "pass_launches": pl.value, "pass_ms": ms.value, "pass_bytes": by.value}
 
     def pass_breakdown(self):
-        la = (C.c_int64 * 3)()
-        ms, by, fl = (C.c_double * 3)(), (C.c_double * 3)(), (C.c_double * 3)()
+        la = (C.c_int64 * 4)()
+        ms, by, fl = (C.c_double * 4)(), (C.c_double * 4)(), (C.c_double * 4)()
         self._ck(self.lib.dlra_pass_breakdown(self.h, la, ms, by, fl))
-        names = ("fused_KL", "K_only", "L_only")
+        names = ("fused_KL", "K_only", "L_only", "pipelined_SKL")
         return {nm: {"launches": la[i], "ms": ms[i], "bytes": by[i], "flops": fl[i]} for i, nm in enumerate(names)}
 
     def event_record(self, slot):
