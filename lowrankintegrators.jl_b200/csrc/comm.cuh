@@ -1,7 +1,7 @@
 // Collectives of the row-sharded multi-GPU path.  The reference is single-process and has no
 // collective; here the partial sums of L / M / S are all-reduced and the TSQR R-factors all-gathered.  Two transports:
 //
-//  * P2P (default on one NVSwitch box): every rank exposes an exchange region through CUDA IPC; a collective is
+//  * P2P (default of the host mirror on one NVSwitch box): every rank exposes an exchange region through CUDA IPC; a collective is
 //    "post my contribution + raise a sequence flag in every peer" followed by ONE kernel that waits for the flags and
 //    reads the peers' contributions directly over NVLink (ld.relaxed.sys on mapped peer pointers), summing them in rank
 //    order — bit-identical on every rank, ~10 us instead of NCCL's small-message latency, no extra copies.
@@ -42,10 +42,12 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
 // copy `count` doubles into the local exchange buffer; the last CTA to finish raises this rank's flag in every peer
 __global__ void __launch_bounds__(256) p2p_post_kernel(P2PView v, const double* __restrict__ src, int64_t count, unsigned int* ticket) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) v.data_local[i] = src[i];
-    __threadfence_system();
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence();   // one cumulative fence per CTA (the barrier ordered the other threads' stores before it)
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (!last) return;
     __threadfence_system();
@@ -131,6 +133,7 @@ struct Comm {
         check(pCommInitRank(&comm, nranks_, id, rank_), "ncclCommInitRank");
         nranks = nranks_;
         rank = rank_;
+        p2p = false;   // an explicit NCCL init selects the NCCL transport
     }
 
     // ---- P2P set-up -----------------------------------------------------------------------------------------------

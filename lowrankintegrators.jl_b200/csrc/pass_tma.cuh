@@ -425,10 +425,12 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
         else L[j + (int64_t)c * ldl] = s + init_term(j, c);
     }
     if (!XR) return;
-    __threadfence_system();
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        __threadfence();   // one cumulative fence per CTA (the barrier ordered the other threads' stores before it)
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
     __syncthreads();
     if (last) {
         __threadfence_system();

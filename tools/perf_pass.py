@@ -26,8 +26,10 @@ def main():
             eng = lri.Engine(n, m, r, rmax=r, rank_adaptive=(alg == "rabug"))
             eng.set_factors(U0, S0, V0)
             eng.data_init(snaps[0])
+            look = len(sys.argv) > 7 and sys.argv[7] == "lookahead" and alg == "bug" and kind == L.DATA_SNAPSHOT
+            if look: eng.data_push(snaps[1], kind)
             def one(i):
-                eng.data_push(snaps[(i + 1) % 3], kind)
+                eng.data_push(snaps[(i + 2) % 3] if look else snaps[(i + 1) % 3], kind)
                 if alg == "bug": eng.step_bug()
                 elif alg == "ksl": eng.step_ksl(L.KSL_PRIMAL)
                 elif alg == "rabug": eng.step_rabug(1e-3, r)
