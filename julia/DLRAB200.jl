@@ -83,6 +83,8 @@ mutable struct B200Cache <: AbstractDLRAlgorithm_Cache
     y            # data stream of a MatrixDataProblem (snapshots on the host or device pointers), else nothing
     n::Int
     m::Int
+    pushed::Int  # snapshots already handed to the engine beyond the current time (0, 1 or 2: one snapshot of lookahead)
+    tf           # end of the time span (no lookahead past it)
 end
 
 function B200Cache(device, n, m, r0, rmax, adaptive::Bool)
@@ -90,7 +92,7 @@ function B200Cache(device, n, m, r0, rmax, adaptive::Bool)
     rc = ccall((:dlra_create, libdlra), Cint, (Cint, Int64, Int64, Cint, Cint, Cint, Ref{Handle}),
                device, n, m, r0, rmax, adaptive ? DLRA_RANK_ADAPTIVE : Cint(0), href)
     rc == 0 || throw(DLRAError(rc, unsafe_string(ccall((:dlra_last_error, libdlra), Cstring, (Handle,), C_NULL))))
-    c = B200Cache(href[], nothing, n, m)
+    c = B200Cache(href[], nothing, n, m, 0, nothing)
     finalizer(x -> ccall((:dlra_destroy, libdlra), Cint, (Handle,), x.h), c)
     return c
 end
@@ -122,6 +124,7 @@ function alg_cache(prob::MatrixDataProblem, w::OnB200, u, dt; t0 = prob.tspan[1]
     c = B200Cache(w.device, n, m, r, max(rmax, r), adaptive)
     set_factors!(c, u)
     c.y = prob.y
+    c.tf = prob.tspan[2]
     y0 = prob.y isa AbstractArray ? prob.y[1] : prob.y(t0)          # yprev (projector_splitting.jl:91)
     check(c.h, ccall((:dlra_data_init_host, libdlra), Cint, (Handle, Ptr{Float64}, Int64), c.h, y0, size(y0, 1)))
     return c
@@ -180,7 +183,15 @@ function step!(integrator::DLRIntegrator, w::OnB200, dt)
             ksl!(c, alg.order isa PrimalLieTrotter ? KSL_PRIMAL : KSL_DUAL, t, dt)
         end
     elseif alg isa UnconventionalAlgorithm
-        isdata && push_data!(c, t, dt)
+        if isdata
+            # update_data! for this step plus one snapshot of lookahead: libdlra then forms the next step's K/L contractions
+            # in the same sweep as this step's core pass (identical results, 3/4 of the HBM reads)
+            c.pushed == 0 && (push_data!(c, t, dt); c.pushed = 1)
+            if c.pushed == 1 && t + 2dt <= c.tf
+                push_data!(c, t, 2dt); c.pushed = 2
+            end
+            c.pushed -= 1
+        end
         check(c.h, ccall((:dlra_step_bug, libdlra), Cint, (Handle, Float64, Float64), c.h, t, dt))
     elseif alg isa RankAdaptiveUnconventionalAlgorithm
         isdata && push_data!(c, t, dt)
@@ -194,6 +205,22 @@ function step!(integrator::DLRIntegrator, w::OnB200, dt)
     integrator.u = get_factors(c)      # the host copy the reference mutates in place
     integrator.t += dt
     integrator.iter += 1
+end
+
+# ---- multi-GPU (one Julia process per GPU, e.g. MPI.jl or Distributed.jl workers) -----------------------------------
+"""
+    attach!(cache, nranks, rank, allgather)
+
+Row-shard the problem: every process passes ITS contiguous row block of `u0.U` and of each snapshot.  `allgather(bytes)`
+is any host-side all-gather of a 64-byte blob (MPI.Allgather, Distributed.jl ...): it hands out the CUDA-IPC handles of the
+peer-to-peer exchange regions (dlra_p2p_export / dlra_p2p_import).  NCCL (dlra_nccl_unique_id / dlra_comm_init) is the
+alternative transport.
+"""
+function attach!(c::B200Cache, nranks::Integer, rank::Integer, allgather)
+    mine = Vector{UInt8}(undef, 64)
+    check(c.h, ccall((:dlra_p2p_export, libdlra), Cint, (Handle, Ptr{UInt8}), c.h, mine))
+    all = allgather(mine)::Vector{UInt8}                      # nranks * 64 bytes, rank order
+    check(c.h, ccall((:dlra_p2p_import, libdlra), Cint, (Handle, Cint, Cint, Ptr{UInt8}), c.h, nranks, rank, all))
 end
 
 end # module

@@ -1,0 +1,118 @@
+"""CPU tests of the host-side mirror (no GPU, no libdlra compute calls): the driver loop semantics of
+src/primitives.jl:68-104 and the data-feed protocol (update_data!, one-snapshot lookahead, Strang's two increments)."""
+import numpy as np
+import pytest
+
+import lowrankintegrators.jl_b200 as lri
+from lowrankintegrators.jl_b200 import api
+
+
+class FakeEngine:
+    """Records the C-ABI calls the mirror would make."""
+    log = []
+
+    def __init__(self, n, m, r0, rmax=None, rank_adaptive=False, device=None, force_generic=False):
+        self.n, self.m, self.r = n, m, r0
+        self.calls = []
+        FakeEngine.log.append(self)
+
+    def set_factors(self, U, S, V):
+        self.calls.append(("set_factors", S.shape[0]))
+
+    def get_factors(self):
+        return np.zeros((self.n, self.r)), np.eye(self.r), np.zeros((self.m, self.r))
+
+    def data_init(self, A0):
+        self.calls.append(("init", float(A0[0, 0])))
+
+    def data_push(self, A, kind=0):
+        self.calls.append(("push", float(A[0, 0])))
+
+    def step_bug(self, t=0.0, dt=1.0):
+        self.calls.append(("bug", t, dt))
+
+    def step_ksl(self, order, t=0.0, dt=1.0):
+        self.calls.append(("ksl", order, t, dt))
+
+    def step_rabug(self, tol, rmax, t=0.0, dt=1.0):
+        self.calls.append(("rabug", t, dt))
+        return self.r, False
+
+    def step_greedy(self, t=0.0, dt=1.0):
+        self.calls.append(("greedy", t, dt))
+
+    def sync(self):
+        pass
+
+
+@pytest.fixture
+def fake(monkeypatch):
+    FakeEngine.log = []
+    monkeypatch.setattr(api, "Engine", FakeEngine)
+    return FakeEngine
+
+
+def _u0(n=6, m=5, r=2):
+    return lri.SVDLikeRepresentation(np.eye(n)[:, :r], np.eye(r), np.eye(m)[:, :r])
+
+
+def _snaps(k, n=6, m=5):
+    return [np.full((n, m), float(i)) for i in range(k)]   # snapshot i is tagged by its value
+
+
+def test_discrete_solve_loop_and_lookahead_pushes(fake):
+    y = _snaps(5)
+    sol = lri.solve(lri.MatrixDataProblem(y, _u0()), lri.UnconventionalAlgorithm())
+    assert sol.t == [1, 2, 3, 4, 5] and len(sol.Y) == 5                      # t0:dt:tf with dt = 1 (primitives.jl:77-80,100-104)
+    calls = fake.log[0].calls
+    assert calls[1] == ("init", 0.0)                                          # yprev = y[1]
+    pushes = [c[1] for c in calls if c[0] == "push"]
+    assert pushes == [1.0, 2.0, 3.0, 4.0]                                     # every snapshot exactly once, in order
+    # lookahead: snapshot k+2 is pushed before step k runs, except at the end of the stream
+    seq = [c[0] if c[0] != "push" else ("p", c[1]) for c in calls[2:]]
+    assert seq == [("p", 1.0), ("p", 2.0), "bug", ("p", 3.0), "bug", ("p", 4.0), "bug", "bug"]
+
+
+def test_lookahead_can_be_disabled_and_other_integrators_push_once(fake):
+    y = _snaps(4)
+    lri.solve(lri.MatrixDataProblem(y, _u0()), lri.UnconventionalAlgorithm(), lookahead=False)
+    seq = [c[0] for c in fake.log[0].calls[2:]]
+    assert seq == ["push", "bug", "push", "bug", "push", "bug"]
+    lri.solve(lri.MatrixDataProblem(y, _u0()), lri.ProjectorSplitting(lri.DualLieTrotter()))
+    seq = [c[0] for c in fake.log[1].calls[2:]]
+    assert seq == ["push", "ksl", "push", "ksl", "push", "ksl"]
+    assert all(c[1] == lri._lib.KSL_DUAL for c in fake.log[1].calls if c[0] == "ksl")
+
+
+def test_continuous_stream_step_count_and_strang_two_increments(fake):
+    seen = []
+
+    def y(t):
+        seen.append(round(t, 10))
+        return np.full((6, 5), t)
+
+    sol = lri.solve(lri.MatrixDataProblem(y, _u0(), (0.0, 0.3)), lri.ProjectorSplitting(lri.Strang()), 0.1)
+    assert len(sol.Y) == 4 and abs(sol.t[-1] - 0.3) < 1e-12                   # floor((tf-t0)/dt)+1 slots (primitives.jl:92-98)
+    assert seen == [0.0, 0.05, 0.1, 0.15, 0.2, 0.25, 0.3]                     # y(t0), then y(t+dt/2), y(t+dt) per step
+    kinds = [c[1] for c in fake.log[0].calls if c[0] == "ksl"]
+    assert kinds == [lri._lib.KSL_PRIMAL, lri._lib.KSL_DUAL] * 3
+
+
+def test_errors_match_the_reference(fake):
+    with pytest.raises(AssertionError):   # reverse time span (projector_splitting.jl:109)
+        lri.solve(lri.MatrixDataProblem(lambda t: np.zeros((6, 5)), _u0(), (1.0, 0.0)), lri.UnconventionalAlgorithm(), 0.1)
+    with pytest.raises(AssertionError):   # function data needs dt (primitives.jl:78)
+        lri.solve(lri.MatrixDataProblem(lambda t: np.zeros((6, 5)), _u0(), (0.0, 1.0)), lri.UnconventionalAlgorithm())
+    with pytest.raises(TypeError):        # Strang on a snapshot vector: update_data! needs Int t/dt (data_integrator.jl:26)
+        lri.solve(lri.MatrixDataProblem(_snaps(3), _u0()), lri.ProjectorSplitting(lri.Strang()))
+
+
+def test_truncated_svd_and_rank_rule():
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((30, 8)) @ np.diag(10.0 ** -np.arange(8)) @ rng.standard_normal((8, 20))
+    u = lri.truncated_svd(A, 3)
+    assert u.rank == 3 and np.allclose(u.U.T @ u.U, np.eye(3))
+    s = np.linalg.svd(A, compute_uv=False)
+    r = lri.truncate_to_tolerance(s, 1e-4)
+    assert np.sqrt(np.sum(s[r:] ** 2)) <= 1e-4 < np.sqrt(np.sum(s[r - 1:] ** 2))
+    assert lri.truncated_svd(A, tol=1e-4).rank == r
