@@ -103,6 +103,15 @@ int dlra_get_factors_host(dlra_handle h, double* U, int64_t ldu, double* S, int6
 int dlra_get_factors(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V,
                      int64_t ldv, int* r);
 int dlra_get_rank(dlra_handle h, int* r);
+/* truncated_svd(A, r) / truncated_svd(A; tol) (LowRankArithmetic; call sites test/data_driven_approximation.jl:18,
+ * examples/generic_matrix.jl:29) for matrices that only exist on the device: randomized subspace
+ * iteration with the engine's own kernels (K-only / L-only passes, TSQR, Jacobi SVD) — A (n_local x m, device) is
+ * streamed 2*(power_iters+1) times, no n x m SVD is formed.  r > 0 fixes the rank; r == 0 picks it from `tol` with the
+ * truncate_to_tolerance rule among the first min(rmax, sketch) values.  sketch = r + oversample columns (<= 128).
+ * The result (an approximation of the reference's exact LAPACK truncation, error within a few % of optimal for
+ * decaying spectra) becomes the engine's factors.  Works row-sharded. */
+int dlra_truncated_svd(dlra_handle h, const double* A, int64_t ld, int r, double tol, int oversample,
+                       int power_iters, uint64_t seed);
 /* borrow the engine's live factor buffers (valid until the next step; ld of U,V = n_local, m; ld of S = rmax cap) */
 int dlra_factor_ptrs(dlra_handle h, const double** U, int64_t* ldu, const double** S, int64_t* lds,
                      const double** V, int64_t* ldv, int* r);

@@ -4,7 +4,7 @@ from . import _lib
 from .api import (DLRIntegrator, DLRSolution, DualLieTrotter, GreedyIntegrator, MatrixDataProblem, MatrixDEProblem,
                   PrimalLieTrotter, ProjectorSplitting, RankAdaptiveUnconventionalAlgorithm, Strang, SubStepper,
                   SVDLikeRepresentation, TwoFactorRepresentation, UnconventionalAlgorithm, init, solve, step,
-                  truncate_to_tolerance, truncated_svd, update_sol)
+                  truncate_to_tolerance, truncated_svd, truncated_svd_device, update_sol)
 from .engine import Engine, colmajor_device, empty_colmajor
 from .rhs import BurgersRHS, FactoredRHS, LinearRHS
 from .distributed import attach_engine, comm_from_torch, row_shard

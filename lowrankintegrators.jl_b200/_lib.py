@@ -41,6 +41,7 @@ SIGNATURES = {
     "dlra_get_factors_host": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_int_p]),
     "dlra_get_factors": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_int_p]),
     "dlra_get_rank": (C.c_int, [handle_t, c_int_p]),
+    "dlra_truncated_svd": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64]),
     "dlra_factor_ptrs": (C.c_int, [handle_t, C.POINTER(C.c_void_p), c_i64_p, C.POINTER(C.c_void_p), c_i64_p,
                                    C.POINTER(C.c_void_p), c_i64_p, c_int_p]),
     "dlra_data_init": (C.c_int, [handle_t, C.c_void_p, C.c_int64]),

@@ -92,6 +92,21 @@ def truncated_svd(A, r: Optional[int] = None, tol: Optional[float] = None) -> SV
     return SVDLikeRepresentation(U[:, :r], np.diag(s[:r]), Vt[:r, :].T)
 
 
+def truncated_svd_device(A, r: Optional[int] = None, tol: Optional[float] = None, rmax: int = 128, oversample: int = 8,
+                         power_iters: int = 2, seed: int = 0, device=None) -> SVDLikeRepresentation:
+    """truncated_svd for a matrix that lives on the GPU (column-major CUDA tensor): randomized subspace iteration with the
+    engine's streaming kernels instead of a host LAPACK SVD of n x m (SURVEY.md §8f item 2).  Approximates the reference's
+    exact truncation (within a few % of the optimal error for decaying spectra; exact for rank(A) <= r)."""
+    n, m = A.shape
+    cap = int(min(rmax if r is None else r, m, 128))
+    eng = Engine(n, m, 1, cap, device=device)
+    try:
+        eng.truncated_svd(A, r or 0, tol or 0.0, oversample, power_iters, seed)
+        return SVDLikeRepresentation(*eng.get_factors())
+    finally:
+        eng.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # problems, solution, integrator  (src/primitives.jl)
 # ------------------------------------------------------------------------------------------------

@@ -666,6 +666,77 @@ extern "C" int dlra_step_greedy(dlra_handle h, double t, double dt) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// initial condition on the device
+// ---------------------------------------------------------------------------------------------------
+// uniform(-1,1) test matrix from a counter-based hash (splitmix64): identical on every rank for a given seed
+__global__ void random_fill_kernel(int64_t rows, int cols, double* __restrict__ X, int64_t ldx, uint64_t seed) {
+    const int64_t tot = rows * cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t z = seed + 0x9E3779B97F4A7C15ull * (uint64_t)(e + 1);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        X[(e % rows) + (e / rows) * ldx] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+}
+
+extern "C" int dlra_truncated_svd(dlra_handle h, const double* A, int64_t ld, int r, double tol, int oversample, int power_iters,
+                                  uint64_t seed) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(A && ld >= h->n, "bad matrix pointer / leading dimension");
+    DLRA_REQUIRE(r >= 0 && r <= h->rmax && oversample >= 0 && power_iters >= 0, "bad rank / oversampling / iteration count");
+    DLRA_REQUIRE(r > 0 || tol >= 0.0, "either a rank or a tolerance is needed");
+    Ctx& cx = h->cx;
+    const int64_t n = h->n, m = h->m;
+    const int l = (int)std::min<int64_t>(std::min<int64_t>((r > 0 ? r : h->rmax) + oversample, 128), m);
+    DLRA_REQUIRE(l >= std::max(r, 1), "sketch narrower than the requested rank");
+    // temporaries: Y (n x l), Z (m x l), small l x l blocks
+    h->isvd.ensure(n * l + m * l + 6 * (int64_t)l * l + l + 64, cx.stream);
+    double* Y = h->isvd.p;
+    double* Z = Y + n * l;
+    double* Rb = Z + m * l;               // l x l, ld l
+    double* Rt = Rb + (int64_t)l * l;     // Rb'
+    double* P = Rt + (int64_t)l * l;
+    double* Wm = P + (int64_t)l * l;
+    double* sg = Wm + (int64_t)l * l;
+    Delta d; d.A = A; d.lda = ld;
+    Side sd = main_side(h);
+    auto qr_cols = [&](double* X, int64_t rows, Comm& cm, double* R) {
+        ensure_qr_ws(sd, rows, l);
+        thin_qr(cx, cm, rows, l, X, rows, X, rows, R, l, h->tws.p, h->gws.p, h->wtmp.p);
+    };
+    random_fill_kernel<<<(unsigned)std::min<int64_t>(cdiv(m * l, 256), 1184), 256, 0, cx.stream>>>(m, l, Z, m, seed);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+    for (int it = 0; it <= power_iters; ++it) {
+        DLRA_CUDA(cudaMemsetAsync(Y, 0, (size_t)n * l * sizeof(double), cx.stream));
+        pass_KL(h, d, l, Z, m, nullptr, 0, Y, n, nullptr, 0);          // Y = A*Z
+        qr_cols(Y, n, h->comm, nullptr);                                // Q = orth(Y)   (row sharded)
+        pass_KL(h, d, l, nullptr, 0, Y, n, nullptr, 0, Z, m);          // Z = A'*Q      (all-reduced)
+        if (it < power_iters) qr_cols(Z, m, h->self, nullptr);          // re-orthonormalise between power iterations
+    }
+    qr_cols(Z, m, h->self, Rb);                                         // A'Q = Qb*Rb  =>  A ~ Q*Rb'*Qb'
+    copy_mat(cx, l, l, Rb, l, true, Rt, l);
+    h->jws.ensure((int64_t)jacobi_ws_doubles(l), cx.stream);
+    const int rcap = std::min(h->rmax, l);
+    jacobi_svd(cx, l, Rt, l, h->jws.p, P, l, sg, Wm, l, tol, rcap, h->r_new_dev, nullptr);   // Rb' = P*diag(sg)*Wm'
+    int rr = r;
+    if (r == 0) {
+        DLRA_CUDA(cudaMemcpyAsync(h->r_new_host, h->r_new_dev, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
+        DLRA_CUDA(cudaStreamSynchronize(cx.stream));
+        rr = *h->r_new_host;
+    }
+    DLRA_REQUIRE(rr >= 1 && rr <= h->rmax, "selected rank outside [1, rmax]");
+    gemm_nn(cx, n, l, rr, Y, n, nullptr, 0, P, l, false, h->U, n, 1.0, 0.0);     // U = Q*P[:, 1:r]
+    gemm_nn(cx, m, l, rr, Z, m, nullptr, 0, Wm, l, false, h->V, m, 1.0, 0.0);    // V = Qb*W[:, 1:r]
+    fill_mat(cx, rr, rr, h->S, h->W, 0.0, 0.0);
+    copy_mat(cx, 1, rr, sg, 1, false, h->S, h->W + 1);                           // S = Diagonal(sigma[1:r])
+    h->r = rr;
+    h->kl_ready = false;
+    DLRA_API_END(h)
+}
+
+// ---------------------------------------------------------------------------------------------------
 // DE problem configuration
 // ---------------------------------------------------------------------------------------------------
 extern "C" int dlra_rhs_set(dlra_handle h, const dlra_operator* A, const dlra_operator* B, const double* G, int64_t ldg,

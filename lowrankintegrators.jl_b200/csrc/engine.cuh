@@ -77,6 +77,7 @@ struct dlra_engine {
     double* scal_dev = nullptr; // 8 doubles of device scalars
     dlra::DevBuf gws, tws, wtmp, jws, nscr, mscr, part;  // grow-on-demand scratch
     dlra::DevBuf gws2, tws2, wtmp2;                       // scratch of the auxiliary stream
+    dlra::DevBuf isvd;                                    // temporaries of dlra_truncated_svd
 
     // data feed
     const double* prev = nullptr; int64_t ldprev = 0;

@@ -123,6 +123,14 @@ class Engine:
         if not hu:
             self.sync()
 
+    def truncated_svd(self, A, r=0, tol=0.0, oversample=8, power_iters=2, seed=0):
+        """Set the engine's factors to a rank-r (or tolerance-selected) truncated SVD of the device matrix A (randomized
+        subspace iteration inside libdlra.so; A is streamed 2*(power_iters+1) times)."""
+        p, ld, host, keep = _ptr_ld(A)
+        assert not host, "truncated_svd takes a device matrix (use api.truncated_svd for host arrays)"
+        self._ck(self.lib.dlra_truncated_svd(self.h, p, ld, int(r or 0), float(tol or 0.0), int(oversample), int(power_iters), int(seed)))
+        return self.rank
+
     def get_factors(self):
         r = self.rank
         U = np.empty((self.n, r), order="F")

@@ -128,3 +128,29 @@ def test_errors_are_loud(lri):
         eng.step_bug()          # no data pushed
     with pytest.raises(lri._lib.DLRAError):
         lri.Engine(64, 32, 4, rmax=2)
+
+
+def test_truncated_svd_device(lri):
+    # initial condition without a host SVD of n x m.  Exact for rank(A) <= r, near-optimal otherwise.
+    import torch
+    rng = np.random.default_rng(5)
+    n, m = 3000, 700
+    Q1, _ = np.linalg.qr(rng.standard_normal((n, 40)))
+    Q2, _ = np.linalg.qr(rng.standard_normal((m, 40)))
+    sig = 2.0 ** -np.arange(40)
+    A = (Q1 * sig) @ Q2.T
+    Ad = torch.from_numpy(np.ascontiguousarray(A.T)).cuda().t()
+    for r in (6, 16, 24):
+        u = lri.truncated_svd_device(Ad, r, oversample=8, power_iters=2)
+        best = np.sqrt(np.sum(sig[r:] ** 2))
+        err = np.linalg.norm(u.full() - A)
+        assert u.rank == r and err <= 1.02 * best, (r, err, best)
+        assert np.linalg.norm(u.U.T @ u.U - np.eye(r)) < 1e-12 and np.linalg.norm(u.V.T @ u.V - np.eye(r)) < 1e-12
+        assert np.allclose(np.diag(u.S), sig[:r], rtol=1e-3)
+    u = lri.truncated_svd_device(Ad, tol=1e-4, rmax=32)
+    ref = O.truncated_svd(A, tol=1e-4)
+    assert u.rank == ref.rank
+    B = (Q1[:, :5] * sig[:5]) @ Q2[:, :5].T           # exactly rank 5: reproduced to round-off
+    Bd = torch.from_numpy(np.ascontiguousarray(B.T)).cuda().t()
+    u = lri.truncated_svd_device(Bd, 5)
+    assert rel_fro(u.full(), B) < 1e-13
