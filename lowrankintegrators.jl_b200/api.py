@@ -144,6 +144,11 @@ class DLRIntegrator:
     def u(self):
         return SVDLikeRepresentation(*self.cache.get_factors())
 
+    def checkpoint(self):
+        """Everything needed to resume (engine state = (U,S,V,r,t,iter) + the data stream position)."""
+        u = self.u
+        return {"U": u.U, "S": u.S, "V": u.V, "t": self.t, "iter": self.iter}
+
 
 def init_sol(dt, t0, tf, u0):  # primitives.jl:92-104
     if isinstance(dt, (int, np.integer)) and not isinstance(dt, bool):
@@ -242,7 +247,7 @@ def _has_snapshot(y, tspan, t, ahead):
     return isinstance(t, (int, np.integer)) and (t + ahead - 1) < len(y) and (t + ahead) <= tspan[1]
 
 
-def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False, lookahead=True) -> DLRIntegrator:
+def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False, lookahead=True, resume=None) -> DLRIntegrator:
     """init(prob, alg, dt): projector_splitting.jl:107-115, unconventional.jl:109-119,
     rank_adaptive_unconventional.jl:94-104, greedy_integrator.jl:49-59.  `comm` = "torch" (use the initialised torch.distributed group to distribute
     a fresh ncclUniqueId) or (nranks, rank, unique_id) row-shards the problem: every rank passes ITS row block of u0.U
@@ -250,6 +255,9 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     t0, tf = prob.tspan
     assert tf > t0, "Integration in reverse time direction is not supported"
     u0 = prob.u0
+    if resume is not None:   # continue from DLRIntegrator.checkpoint(): factors and time come from the saved state
+        u0 = SVDLikeRepresentation(resume["U"], resume["S"], resume["V"])
+        t0 = resume["t"]
     n, r0 = u0.U.shape
     m = u0.V.shape[0]
     adaptive = isinstance(alg, RankAdaptiveUnconventionalAlgorithm)
@@ -266,7 +274,7 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     eng.set_factors(u0.U, u0.S, u0.V)  # deepcopy(prob.u0)
     if isinstance(prob, MatrixDataProblem):
         y = prob.y
-        eng.data_init(y(t0) if callable(y) else y[0])  # yprev = y[1] | y(t0)
+        eng.data_init(y(t0) if callable(y) else y[int(t0 - prob.tspan[0])])  # yprev = y[1] | y(t0) (snapshot at the start time)
     else:
         if isinstance(alg, GreedyIntegrator):
             raise TypeError("MethodError: GreedyIntegrator is defined for data problems")
@@ -278,6 +286,8 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     sol.Y[0] = u0.copy() if hasattr(u0, "copy") else u0
     integ = DLRIntegrator(eng, t0, dt, sol, alg, type(prob), prob, save_everystep)
     integ.lookahead = bool(lookahead)
+    if resume is not None:
+        integ.iter = 0   # sol restarts at the checkpoint; resume["iter"] tells the caller where that was
     return integ
 
 

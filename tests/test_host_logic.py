@@ -116,3 +116,19 @@ def test_truncated_svd_and_rank_rule():
     r = lri.truncate_to_tolerance(s, 1e-4)
     assert np.sqrt(np.sum(s[r:] ** 2)) <= 1e-4 < np.sqrt(np.sum(s[r - 1:] ** 2))
     assert lri.truncated_svd(A, tol=1e-4).rank == r
+
+
+def test_checkpoint_resume_restarts_the_stream_at_the_saved_time(fake):
+    y = _snaps(6)
+    prob = lri.MatrixDataProblem(y, _u0())
+    integ = lri.init(prob, lri.UnconventionalAlgorithm(), 1)
+    for _ in range(2):
+        lri.step(integ)
+    state = integ.checkpoint()
+    assert state["t"] == 3 and state["iter"] == 2
+    integ2 = lri.init(prob, lri.UnconventionalAlgorithm(), 1, resume=state)
+    assert integ2.t == 3
+    calls = fake.log[1].calls
+    assert calls[1] == ("init", 2.0)          # yprev = y[3] (value 2.0), the snapshot at the checkpoint time
+    lri.step(integ2)
+    assert [c[1] for c in calls if c[0] == "push"][:2] == [3.0, 4.0]
