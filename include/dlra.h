@@ -159,6 +159,10 @@ int dlra_step_rabug(dlra_handle h, double t, double dt, double tol, int64_t rmax
 int dlra_step_greedy(dlra_handle h, double t, double dt);
 
 int dlra_sync(dlra_handle h);
+/* The engine runs on its own (non-blocking) stream.  Device buffers handed to it must be complete: either synchronise the
+ * producing stream on the host, or call this with that stream (a cudaStream_t; NULL = the legacy default stream) — the
+ * engine stream then waits for everything enqueued there so far (event record + cudaStreamWaitEvent, no host blocking). */
+int dlra_wait_stream(dlra_handle h, void* producer_stream);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* ‖U·S·Vᵀ − Yref‖_F / ‖Yref‖_F without materialising n x m on the host (Yref: n_local x m device);

@@ -56,6 +56,7 @@ SIGNATURES = {
     "dlra_step_rabug": (C.c_int, [handle_t, C.c_double, C.c_double, C.c_double, C.c_int64, c_int_p, c_int_p]),
     "dlra_step_greedy": (C.c_int, [handle_t, C.c_double, C.c_double]),
     "dlra_sync": (C.c_int, [handle_t]),
+    "dlra_wait_stream": (C.c_int, [handle_t, C.c_void_p]),
     "dlra_reconstruct_error": (C.c_int, [handle_t, C.c_void_p, C.c_int64, c_double_p]),
     "dlra_reconstruct": (C.c_int, [handle_t, C.c_void_p, C.c_int64]),
     "dlra_stats": (C.c_int, [handle_t, c_i64_p, c_i64_p, c_double_p, c_double_p, C.c_int]),

@@ -108,6 +108,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     de_release(h);
     h->gws2.release(); h->tws2.release(); h->wtmp2.release();
     cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+    if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     cudaStreamDestroy(h->cx.stream); cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->ax.stream);
     delete h;
     return DLRA_OK;
@@ -116,6 +117,15 @@ extern "C" int dlra_destroy(dlra_handle h) {
 extern "C" int dlra_sync(dlra_handle h) {
     DLRA_API_BEGIN(h)
     DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_wait_stream(dlra_handle h, void* producer_stream) {
+    DLRA_API_BEGIN(h)
+    if (!h->ev_ext) DLRA_CUDA(cudaEventCreateWithFlags(&h->ev_ext, cudaEventDisableTiming));
+    DLRA_CUDA(cudaEventRecord(h->ev_ext, (cudaStream_t)producer_stream));
+    DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->ev_ext, 0));
+    DLRA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_ext, 0));
     DLRA_API_END(h)
 }
 
@@ -349,6 +359,18 @@ static void qr_nside(dlra_handle h, double* A, int C, double* R) {
     ensure_qr_ws(sd, h->n, C);
     thin_qr(h->cx, h->comm, h->n, C, A, h->n, A, h->n, R, h->W, h->tws.p, h->gws.p, h->wtmp.p);
 }
+// thin QR of (A + Ua*Sa) in place; the rank-r update rides on the panel load of the first TSQR level when it can
+static void qr_nside_plus(dlra_handle h, double* A, int C, const double* Ua, const double* Sa, int k) {
+    if (C <= TSQR_MAXC && h->n > 128) {
+        Side sd = main_side(h);
+        ensure_qr_ws(sd, h->n, C);
+        TsqrAdd add; add.U = Ua; add.ldu = h->n; add.S = Sa; add.lds = h->W; add.k = k;
+        tsqr(h->cx, h->comm, h->n, C, A, h->n, A, h->n, nullptr, h->W, h->tws.p, add);
+    } else {
+        gemm_nn(h->cx, h->n, k, C, Ua, h->n, nullptr, 0, Sa, h->W, false, A, h->n, 1.0, 1.0);
+        qr_nside(h, A, C, nullptr);
+    }
+}
 // thin QR of an m-side (replicated) matrix, in place, computed redundantly on every rank
 static void qr_mside(dlra_handle h, Side sd, double* A, int C, double* R) {
     ensure_qr_ws(sd, h->m, C);
@@ -413,7 +435,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     const bool pre = sc.is_data && h->kl_ready && h->kl_rank == r;   // formed by the previous step's pipelined pass
     h->kl_ready = false;
     if (pre) {
-        gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 1.0);                        // K = ΔA*V0 + U0*S0
+        // K = ΔA*V0 (already in UB) + U0*S0: the update is folded into the TSQR panel load below
         l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, h->kl_ldlp * 16, h->V, m, h->S, W, r, L, m);  // L = ΔA'*U0 + V0*S0'
     } else {
         gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);
@@ -429,7 +451,8 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     fork_aux(h);                                          // m-side chain on the auxiliary stream ...
     qr_mside(h, aux_side(h), L, r, nullptr);              // V1 = qr(L).Q
     gram_mside(h, aux_side(h), r, r, L, h->V, h->N);      // N = V1'*V0
-    qr_nside(h, K, r, nullptr);                           // ... overlaps U1 = qr(K).Q
+    if (pre) qr_nside_plus(h, K, r, h->U, h->S, r);       // ... overlaps U1 = qr(ΔA*V0 + U0*S0).Q
+    else qr_nside(h, K, r, nullptr);                      //              U1 = qr(K).Q
     gram_nside_local(h, r, r, K, h->U, h->M);             // M = U1'*U0 (local rows; summed over ranks below)
     join_aux(h);
     if (sc.is_data) {
@@ -453,9 +476,10 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
             pass_S(h, sc.d, r, r, K, n, L, m, h->Rm, W);        // Rm = U1'*ΔA*V1 (local rows)
         }
         allreduce_pair(h, h->M, r, r, h->Rm, r, r);             // M and the core increment share one collective
-        small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);   // T1 = M*S0
-        small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);   // Sh = M*S0*N'
-        copy_mat(cx, r, r, h->Rm, W, false, h->Sh, W, 1.0, 1.0);
+        core_update(cx, r, r, r, h->M, h->S, h->N, h->Rm, h->S, (int)W, h->T1);   // S1 = M*S0*N' + U1'*ΔA*V1 (one launch)
+        std::swap(h->U, h->UB);
+        std::swap(h->V, h->VB);
+        return;
     } else {
         small_gemm(cx, r, r, r, h->M, (int)W, false, h->S, (int)W, false, h->T1, (int)W, 1.0, 0.0);
         small_gemm(cx, r, r, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);

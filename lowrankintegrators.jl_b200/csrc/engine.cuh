@@ -61,7 +61,7 @@ struct dlra_engine {
     int W = 0;                  // widest factor block (rmax, or 2*rmax when rank adaptive)
     dlra::Ctx cx;
     dlra::Ctx ax;               // auxiliary stream: the replicated m-side chain (QR(L), N) overlaps the n-side chain (QR(K), M)
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ext = nullptr;
     dlra::Comm comm;            // row-shard communicator
     dlra::Comm self;            // nranks = 1: for replicated (m-side) factorizations
     cudaStream_t copy_stream = nullptr;

@@ -273,6 +273,34 @@ inline void small_gemm(Ctx& cx, int p, int q, int k, const double* A, int lda, b
     DLRA_CUDA(cudaGetLastError());
 }
 
+// Core update of the BUG-type integrators in ONE single-CTA launch:  Out = M*S0*N' (+ Add)
+// (unconventional.jl:154 `set_u!(SIntegrator, M*u.S*N')` followed by the S-step increment).  M: p x r, S0: r x r, N: q x r,
+// Add/Out: p x q, all with leading dimension ld; T (p x r, dense) is scratch.  Out may alias S0 (S0 is only read in phase 1).
+__global__ void __launch_bounds__(1024) core_update_kernel(int p, int q, int r, const double* __restrict__ M, const double* __restrict__ S0,
+                                                           const double* __restrict__ N, const double* __restrict__ Add,
+                                                           double* __restrict__ Out, int ld, double* __restrict__ T) {
+    for (int e = threadIdx.x; e < p * r; e += blockDim.x) {
+        const int i = e % p, k = e / p;
+        double s = 0.0;
+        for (int l = 0; l < r; ++l) s = fma(M[i + (int64_t)l * ld], S0[l + (int64_t)k * ld], s);
+        T[e] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < p * q; e += blockDim.x) {
+        const int i = e % p, j = e / p;
+        double s = Add ? Add[i + (int64_t)j * ld] : 0.0;
+        double t = 0.0;
+        for (int k = 0; k < r; ++k) t = fma(T[i + (int64_t)k * p], N[j + (int64_t)k * ld], t);
+        Out[i + (int64_t)j * ld] = t + s;
+    }
+}
+inline void core_update(Ctx& cx, int p, int q, int r, const double* M, const double* S0, const double* N, const double* Add, double* Out,
+                        int ld, double* T) {
+    core_update_kernel<<<1, 1024, 0, cx.stream>>>(p, q, r, M, S0, N, Add, Out, ld, T);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
 // dst[rows x cols] (ldd) = alpha * op(src) (+ beta*dst)   — copies, transposes, scaled adds of small/tall matrices
 __global__ void copy_mat_kernel(int64_t rows, int cols, const double* __restrict__ src, int64_t lds, int trans,
                                 double* __restrict__ dst, int64_t ldd, double alpha, double beta) {

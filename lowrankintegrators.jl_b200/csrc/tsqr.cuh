@@ -198,10 +198,18 @@ __device__ __noinline__ void tsqr_level1(double* stack, double* stack2, double* 
         for (int q = 0; q < RPL1; ++q) stack[c * SLD + lane + 32 * q] = b[q][c];
 }
 
+// optional rank-k update applied while the panel is loaded:  A + Ua*Sa  (the `mul!(US, u.U, u.S)` of the K-step,
+// unconventional.jl:137, folded into the factorisation so K is not re-read and re-written by a separate GEMM)
+struct TsqrAdd {
+    const double* U = nullptr; int64_t ldu = 0;   // rows x k
+    const double* S = nullptr; int64_t lds = 0;   // k x C
+    int k = 0;
+};
+
 template <int CP>
 __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows, int C, const double* __restrict__ A, int64_t lda,
                                                                   double* __restrict__ Q, int64_t ldq,
-                                                                  double* __restrict__ Rstack, int64_t ldr) {
+                                                                  double* __restrict__ Rstack, int64_t ldr, TsqrAdd add) {
     using SM = TsqrSmem<CP>;
     constexpr int RPL0 = TSQR_RPL0;
     constexpr int SLD = SM::SROWS + 1;
@@ -225,6 +233,27 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows,
 #pragma unroll
             for (int q = 0; q < RPL0; ++q) a[q][c] = (ok[q] && c < C) ? col[32 * q] : 0.0;
             col += lda;
+        }
+        if (add.U) {
+            // stage Sa (k x C) in the (still unused) stack area, then a[q][:] += Ua[row, :] * Sa
+            for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) {
+                const int kk = e / CP, c = e % CP;
+                stack[e] = (kk < add.k && c < C) ? add.S[kk + (int64_t)c * add.lds] : 0.0;
+            }
+            __syncthreads();
+#pragma unroll 1
+            for (int kk = 0; kk < add.k; ++kk) {
+                double u[RPL0];
+#pragma unroll
+                for (int q = 0; q < RPL0; ++q) u[q] = ok[q] ? add.U[row0 + lane + 32 * q + (int64_t)kk * add.ldu] : 0.0;
+#pragma unroll
+                for (int c = 0; c < CP; ++c) {
+                    const double sv = stack[kk * CP + c];
+#pragma unroll
+                    for (int q = 0; q < RPL0; ++q) a[q][c] = fma(u[q], sv, a[q][c]);
+                }
+            }
+            __syncthreads();   // the stack area is reused for the R factors below
         }
         reg_panel_qr<CP, RPL0>(a, mypark, PROWS, taus + warp * CP, lane);
         // R_w -> rows [CP*warp, CP*warp + CP) of the stack (zeros below the diagonal)
@@ -334,8 +363,10 @@ inline int64_t tsqr_ws_size(int64_t rows, int C, int nranks) {
     return total + 1024;
 }
 
-inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* Rstack, int64_t ldr) {
+inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* Rstack, int64_t ldr,
+                       const TsqrAdd& add = TsqrAdd()) {
     if (rows <= 128) {
+        DLRA_REQUIRE(add.U == nullptr, "fused rank-k update is only available on the multi-warp TSQR level");
         if (CP == 8) tsqr_small_kernel<8><<<1, 32, 0, cx.stream>>>((int)rows, C, A, lda, Q, ldq, Rstack, ldr);
         else tsqr_small_kernel<16><<<1, 32, 0, cx.stream>>>((int)rows, C, A, lda, Q, ldq, Rstack, ldr);
         cx.launches++;
@@ -349,8 +380,8 @@ inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, in
         DLRA_CUDA(cudaFuncSetAttribute(tsqr_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<16>::BYTES));
         attr_set = true;
     }
-    if (CP == 8) tsqr_reg_kernel<8><<<nb, TSQR_NW * 32, TsqrSmem<8>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr);
-    else tsqr_reg_kernel<16><<<nb, TSQR_NW * 32, TsqrSmem<16>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr);
+    if (CP == 8) tsqr_reg_kernel<8><<<nb, TSQR_NW * 32, TsqrSmem<8>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr, add);
+    else tsqr_reg_kernel<16><<<nb, TSQR_NW * 32, TsqrSmem<16>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr, add);
     cx.launches++;
     DLRA_CUDA(cudaGetLastError());
 }
@@ -365,13 +396,14 @@ inline void apply_blocks(Ctx& cx, int CP, int64_t rows, int C, double* Q, int64_
 
 // Local (single GPU) TSQR of A (rows x C, C <= 16): Q (rows x C, may alias A).  Returns a pointer (inside ws) to the
 // CP x CP padded R factor (ld = CP).  ws must hold tsqr_ws_size doubles.
-inline double* tsqr_local(Ctx& cx, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* ws) {
+inline double* tsqr_local(Ctx& cx, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* ws,
+                          const TsqrAdd& add = TsqrAdd()) {
     const int CP = tsqr_cp(C);
     const int64_t nb = cdiv(rows, TSQR_BR);
     double* Rstack = ws;                    // (nb*CP) x CP, ld = nb*CP
     double* Qtop = ws + nb * CP * CP;       // same shape
     double* rest = Qtop + nb * CP * CP;
-    tsqr_level(cx, CP, rows, C, A, lda, Q, ldq, Rstack, nb * CP);
+    tsqr_level(cx, CP, rows, C, A, lda, Q, ldq, Rstack, nb * CP, add);
     if (nb == 1) return Rstack;
     double* Rtop = tsqr_local(cx, nb * CP, CP, Rstack, nb * CP, Qtop, nb * CP, rest);
     apply_blocks(cx, CP, rows, C, Q, ldq, TSQR_BR, Qtop, nb * CP, CP);
@@ -380,11 +412,11 @@ inline double* tsqr_local(Ctx& cx, int64_t rows, int C, const double* A, int64_t
 
 // Distributed TSQR: rows are this rank's shard.  R (C x C, ldr) optional output (replicated on all ranks).
 inline void tsqr(Ctx& cx, Comm& comm, int64_t rows, int C, const double* A, int64_t lda, double* Q, int64_t ldq, double* R, int64_t ldr,
-                 double* ws) {
+                 double* ws, const TsqrAdd& add = TsqrAdd()) {
     DLRA_REQUIRE(C >= 1 && C <= TSQR_MAXC, "tsqr panel width must be 1..16");
     const int CP = tsqr_cp(C);
     double* tail = ws + tsqr_ws_size(rows, C, comm.nranks) - 1024 - (int64_t)(comm.nranks + 1) * CP * CP * 4;
-    double* Rloc = tsqr_local(cx, rows, C, A, lda, Q, ldq, ws);
+    double* Rloc = tsqr_local(cx, rows, C, A, lda, Q, ldq, ws, add);
     const double* Rfin = Rloc;
     if (comm.nranks > 1) {
         const int G = comm.nranks;

@@ -80,6 +80,12 @@ class Engine:
     def _ck(self, rc):
         L.check(self.h, rc)
 
+    def _after_torch(self):
+        """Device tensors are produced on torch's current stream, the engine runs on its own: make the engine stream wait
+        for everything torch has enqueued so far (no host blocking)."""
+        if torch is not None and torch.cuda.is_available():
+            self._ck(self.lib.dlra_wait_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
     # -- multi-GPU ---------------------------------------------------------------------------------
     def comm_init(self, nranks, rank, unique_id: bytes):
         buf = C.create_string_buffer(unique_id, 128)
@@ -119,6 +125,8 @@ class Engine:
         pv, ldv, hv, kv = _ptr_ld(V)
         assert hu == hs == hv, "U, S, V must all live on the host or all on the device"
         fn = self.lib.dlra_set_factors_host if hu else self.lib.dlra_set_factors
+        if not hu:
+            self._after_torch()
         self._ck(fn(self.h, pu, ldu, ps, lds, pv, ldv, r))
         if not hu:
             self.sync()
@@ -128,6 +136,7 @@ class Engine:
         subspace iteration inside libdlra.so; A is streamed 2*(power_iters+1) times)."""
         p, ld, host, keep = _ptr_ld(A)
         assert not host, "truncated_svd takes a device matrix (use api.truncated_svd for host arrays)"
+        self._after_torch()
         self._ck(self.lib.dlra_truncated_svd(self.h, p, ld, int(r or 0), float(tol or 0.0), int(oversample), int(power_iters), int(seed)))
         return self.rank
 
@@ -152,6 +161,8 @@ class Engine:
     def data_init(self, A0):
         p, ld, host, keep = _ptr_ld(A0)
         fn = self.lib.dlra_data_init_host if host else self.lib.dlra_data_init
+        if not host:
+            self._after_torch()
         self._ck(fn(self.h, p, ld))
         if host:
             self.sync_copies = True
@@ -160,6 +171,8 @@ class Engine:
     def data_push(self, A, kind=L.DATA_SNAPSHOT):
         p, ld, host, keep = _ptr_ld(A)
         fn = self.lib.dlra_data_push_host if host else self.lib.dlra_data_push
+        if not host:
+            self._after_torch()
         self._ck(fn(self.h, p, ld, kind))
         # borrowed device pointers must outlive the step after next (plus one snapshot of lookahead): keep the last four alive
         self._keep["cur3"] = (self._keep.get("cur3", ()) + (keep,))[-4:]
@@ -190,6 +203,7 @@ class Engine:
             o.ld = x.stride(1) if x.shape[1] > 1 else x.shape[0]
             return o
 
+        self._after_torch()
         ops = [op(A), op(B), op(D1), op(D2)]
         refs = [C.byref(o) if o is not None else None for o in ops]
         q = 0
@@ -226,6 +240,7 @@ class Engine:
     def reconstruct_error(self, Yref):
         p, ld, host, keep = _ptr_ld(Yref)
         assert not host, "reconstruct_error takes a device matrix"
+        self._after_torch()
         out = C.c_double()
         self._ck(self.lib.dlra_reconstruct_error(self.h, p, ld, C.byref(out)))
         return out.value
