@@ -449,9 +449,10 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
 
 // Lout chunk (m x rc) = Σ_parts (+ Σ_ranks) + Vi·Siᵀ ; picks the fused kernel when it can (single GPU or P2P transport)
 inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, int64_t ldlp, int64_t part_stride, const double* Vi,
-                       int64_t ldvi, const double* Si, int64_t ldsi, int rk, double* L, int64_t ldl) {
-    Ctx& cx = e->cx;
+                       int64_t ldvi, const double* Si, int64_t ldsi, int rk, double* L, int64_t ldl, Ctx* on = nullptr) {
+    Ctx& cx = on ? *on : e->cx;   // single-GPU runs may place this L-side kernel on the auxiliary stream
     Comm& cm = e->comm;
+    DLRA_REQUIRE(on == nullptr || cm.nranks <= 1, "collectives stay on the main stream");
     const int64_t total = e->m * (int64_t)rc;
     // the cross-rank variant spins on peer flags, so its whole grid must be co-resident (256 threads, <= 16 KB smem: >= 4 CTAs/SM)
     const bool xr = cm.nranks > 1 && cm.p2p;
