@@ -1,6 +1,6 @@
 // Fused streaming contraction over the dense increment ΔA (n x m, column-major) for sm_100a:
 //     K[rows, c] += Σ_j ΔA[rows, j]·Vf[j, c]          (K-use, complete per row panel)
-//     Lpart[panel][j, c] = Σ_{rows∈panel} ΔA[rows, j]·Uf[rows, c]   (L-use, reduced over panels afterwards)
+//     Lpart[cta][j, c] = Σ_{rows of the CTA's panels} ΔA[rows, j]·Uf[rows, c]   (L-use, per-CTA running partial, reduced afterwards)
 // in ONE read of ΔA.  ΔA = A − Aprev is formed in shared memory when a previous snapshot is given
 // (`Δy .= ycurr - yprev`, projector_splitting.jl:119-121), so the increment never exists in HBM.
 //
@@ -13,8 +13,9 @@
 //    L-use) read shared memory bank-conflict free.
 //  * math runs on the fp64 tensor pipe: mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4 — tcgen05/UMMA has no f64 kind).
 //    Each of the 8 consumer warps owns 8 rows of every stage for both uses; K accumulators stay in registers
-//    for the whole panel, L accumulators for one column tile, then an in-CTA reduction over the 8 warps and a
-//    deterministic fixed-order reduction over panels (no atomics).
+//    for the whole panel, L accumulators for one column tile; a reducer warp of the service warpgroup sums the 8 warps'
+//    tiles (mbarrier hand-off, no CTA barrier) into one running partial per CTA, and l_finalize_kernel reduces the
+//    per-CTA partials in fixed order (deterministic, no atomics).
 //  * r is processed in chunks of RT in {8, 16} factor columns: at RT = 16 the pass is already fp64-bound
 //    (AI = r/2 flop/B vs a ridge of ~5.6), so wider ranks re-stream ΔA per chunk at no cost in time.
 #pragma once
@@ -38,7 +39,6 @@ struct PassParams {
     int npanels;
     int ntj;         // column tiles
     double* K; int64_t ldk;       // K-use output (+=), may be null
-    const double* Kin;            // unused
     double* Lpart; int64_t ldlp;  // [gridDim.x][ldlp x RT] per-CTA partial L (ldlp >= m), may be null
 };
 
@@ -364,7 +364,7 @@ inline void launch_pass(dlra_engine* e, const Delta& d, int rc, const double* Vf
     CUtensorMap mapV = DO_K ? make_map_2d(Vf, e->m, rc, ldv, 16, RT, true) : mapA;
     PassParams prm;
     prm.n = e->n; prm.m = e->m; prm.rc = rc; prm.nsub = nsub; prm.npanels = npanels; prm.ntj = (int)cdiv(e->m, PT_TJ);
-    prm.K = K; prm.ldk = ldk; prm.Kin = nullptr; prm.Lpart = Lpart; prm.ldlp = ldlp;
+    prm.K = K; prm.ldk = ldk; prm.Lpart = Lpart; prm.ldlp = ldlp;
     const int grid = std::min(npanels, e->cx.num_sms);
     const double bytes = (double)e->n * (double)e->m * 8.0 * (DIFF ? 2.0 : 1.0);
     const double flops = 2.0 * (double)e->n * (double)e->m * rc * ((DO_K ? 1 : 0) + (DO_L ? 1 : 0));
