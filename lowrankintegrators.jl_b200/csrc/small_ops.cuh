@@ -143,7 +143,7 @@ inline void reduce_parts(Ctx& cx, int p, int q, int nchunks, const double* part,
 // tiles are summed in shared memory, every CTA stores one partial and the LAST CTA to finish (ticket counter) adds the
 // partials in fixed order — deterministic without a second launch.
 // ------------------------------------------------------------------------------------------------
-constexpr int GRAM_ROWS_PER_CTA = 512;
+constexpr int GRAM_ROWS_PER_CTA = 256;
 __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
                                                         const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
                                                         double alpha, double beta, double* __restrict__ part, unsigned int* __restrict__ counters) {

@@ -84,8 +84,12 @@ __device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, i
             const double ss = __shfl_sync(0xffffffffu, h, 0);
             double t = 0.0, scale = 0.0, beta = alpha;
             if (ss > 0.0) {
-                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-                t = (beta - alpha) / beta;
+                // dlarfg with one rsqrt and one reciprocal on the dependent chain: beta = -sign(alpha)*||x||,
+                // tau = (beta - alpha)/beta = 1 + |alpha|/||x||, scale = 1/(alpha - beta)
+                const double nrm2 = fma(alpha, alpha, ss);
+                const double rn = rsqrt(nrm2);
+                beta = -copysign(nrm2 * rn, alpha);
+                t = fma(fabs(alpha), rn, 1.0);
                 scale = 1.0 / (alpha - beta);
             }
             if (lane == 0) tau_s[j] = t;
