@@ -22,7 +22,7 @@
 
 namespace dlra {
 
-constexpr int TSQR_NW = 8;      // warps per CTA
+constexpr int TSQR_NW = 8;      // warps per CTA (4 gives the same step time with one more tree level)
 constexpr int TSQR_RPL0 = 4;    // rows per lane at level 0 (128-row panels)
 constexpr int TSQR_BR = TSQR_NW * 32 * TSQR_RPL0;  // 1024 rows per CTA
 constexpr int TSQR_MAXC = 16;
