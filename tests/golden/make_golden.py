@@ -15,7 +15,7 @@ from tests.problems import lowrank_stream, skew_pair  # noqa: E402
 
 def main():
     out = {}
-    n, m, r, nsnap = 96, 64, 5, 5
+    n, m, r, nsnap = 64, 48, 5, 4
     A = lowrank_stream(n, m, 9, seed=42, eps=1e-3)
     snaps = [A(0.07 * k) for k in range(nsnap)]
     X0 = O.truncated_svd(snaps[0], r)
