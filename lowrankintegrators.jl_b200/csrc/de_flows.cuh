@@ -382,6 +382,7 @@ inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N
         for (int j = 0; j < 7; ++j) { el.k[j] = ks[j]; el.c[j] = h * TS_BT[j]; }
         lincomb(cx, N, nullptr, el, etmp);
         const double EEst = rms_scaled(e, w, N, etmp, X, unew, st.abstol, st.reltol);
+        DLRA_REQUIRE(std::isfinite(EEst), "non-finite state in the adaptive sub-stepper (diverged earlier step or bad input)");
         if (EEst <= 1.0) {
             const double q11 = pow(std::max(EEst, 1e-30), beta1);
             double q = q11 / pow(st.qold, beta2);

@@ -203,7 +203,6 @@ class Engine:
             o.ld = x.stride(1) if x.shape[1] > 1 else x.shape[0]
             return o
 
-        self._after_torch()
         ops = [op(A), op(B), op(D1), op(D2)]
         refs = [C.byref(o) if o is not None else None for o in ops]
         q = 0
@@ -215,6 +214,7 @@ class Engine:
             q = G.shape[1]
             pg, ldg = G.data_ptr(), (G.stride(1) if q > 1 else G.shape[0])
             ph, ldh = H.data_ptr(), (H.stride(1) if q > 1 else H.shape[0])
+        self._after_torch()  # after every layout conversion above has been queued on torch's stream
         self._ck(self.lib.dlra_rhs_set(self.h, refs[0], refs[1], pg, ldg, ph, ldh, q, refs[2], refs[3], float(c_had)))
         self._keep["rhs"] = (keep, ops)
 
