@@ -157,6 +157,17 @@ int dlra_step_rabug(dlra_handle h, double t, double dt, double tol, int64_t rmax
 /* greedy_step!(::SVDLikeRepresentation, ..., ::MatrixDataProblem) (greedy_integrator.jl:94-104):
  * re-projection on the full pushed snapshot X (must be pushed as DLRA_DATA_SNAPSHOT). */
 int dlra_step_greedy(dlra_handle h, double t, double dt);
+/* greedy_step!(::TwoFactorRepresentation, ...) (greedy_integrator.jl:72-92), u = U*Z'.  The engine keeps Z in the V slot
+ * and S at identity (set the factors as (U, I, Z); dlra_get_factors returns (U, I, Z), dlra_reconstruct gives U*Z').
+ *   DLRA_GREEDY_DATA   (MatrixDataProblem, :84-92):   Z = X'*U with the full pushed snapshot X
+ *   DLRA_GREEDY_HYBRID (MatrixHybridProblem, :72-82): Z advanced over [t, t+dt] by dZ/dt = F(U*Z')'*U with the right-hand
+ *       side installed by dlra_rhs_set (the FZ of test/data_informed_approximation.jl:75) and the sub-stepper configured
+ *       for DLRA_FLOW_L; the pushed snapshot is X = y(t+dt)
+ * then U = Q*P' of svd(X*Z) (the orthogonal polar factor; TSQR + small SVD here).
+ * carry_fsal != 0 keeps the Z integrator's cached first stage across calls like the reference's ZIntegrator, which is
+ * never set_u!-ed (the stage was evaluated with the previous basis); 0 re-evaluates it with the current U. */
+enum { DLRA_GREEDY_DATA = 0, DLRA_GREEDY_HYBRID = 1 };
+int dlra_step_greedy_two_factor(dlra_handle h, int mode, int carry_fsal, double t, double dt);
 
 int dlra_sync(dlra_handle h);
 /* The engine runs on its own (non-blocking) stream.  Device buffers handed to it must be complete: either synchronise the
@@ -168,6 +179,13 @@ int dlra_wait_stream(dlra_handle h, void* producer_stream);
 /* ‖U·S·Vᵀ − Yref‖_F / ‖Yref‖_F without materialising n x m on the host (Yref: n_local x m device);
  * with row sharding both norms are all-reduced.  Synchronises. */
 int dlra_reconstruct_error(dlra_handle h, const double* Yref, int64_t ld, double* rel_fro);
+/* normal_component (utils.jl:2-20): N = (I − U·Uᵀ)·dY·(I − Z·pinv(C, atol = tol)·Zᵀ) with Z = V·Sᵀ of the current factors
+ * (Z itself for the two-factor convention S = I) and C = ZᵀZ unless a device r x r matrix C is given.  dY: n_local x m
+ * device.  fro_norm (host, may be NULL) receives ‖N‖_F over all row shards; out (device n_local x m, may be NULL)
+ * receives N.  Two streaming passes over dY (one fused K/L contraction, one rank-2r downdate); discards a pending
+ * lookahead contraction of the pipelined BUG step.  Synchronises when fro_norm is requested. */
+int dlra_normal_component(dlra_handle h, const double* dY, int64_t ld, const double* C, int64_t ldc, double tol, double* out,
+                          int64_t ldo, double* fro_norm);
 /* dense reconstruction Y = U·S·Vᵀ into a device buffer (Matrix(u), LowRankArithmetic) */
 int dlra_reconstruct(dlra_handle h, double* Y, int64_t ld);
 /* number of kernels this handle launched so far / device ms of the dominant contraction kernel

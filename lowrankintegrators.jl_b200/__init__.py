@@ -2,6 +2,7 @@
 Host-side mirror of the reference API (api.py) over the C ABI of libdlra.so (include/dlra.h)."""
 from . import _lib
 from .api import (DLRIntegrator, DLRSolution, DualLieTrotter, GreedyIntegrator, MatrixDataProblem, MatrixDEProblem,
+                  MatrixHybridProblem, normal_component,
                   PrimalLieTrotter, ProjectorSplitting, RankAdaptiveUnconventionalAlgorithm, Strang, SubStepper,
                   SVDLikeRepresentation, TwoFactorRepresentation, UnconventionalAlgorithm, init, solve, step,
                   truncate_to_tolerance, truncated_svd, truncated_svd_device, update_sol)

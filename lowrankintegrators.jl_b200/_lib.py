@@ -16,6 +16,7 @@ RANK_ADAPTIVE, FORCE_GENERIC = 1, 2
 KSL_PRIMAL, KSL_DUAL, KSL_STRANG = 0, 1, 2
 DATA_SNAPSHOT, DATA_DELTA = 0, 1
 FLOW_K, FLOW_S, FLOW_L = 0, 1, 2
+GREEDY_DATA, GREEDY_HYBRID = 0, 1
 ODE_EULER, ODE_RK4, ODE_TSIT5_FIXED, ODE_TSIT5 = 0, 1, 2, 3
 OP_NONE, OP_DENSE, OP_CSR, OP_IDENTITY_SCALED = 0, 1, 2, 3
 
@@ -55,6 +56,9 @@ SIGNATURES = {
     "dlra_step_bug": (C.c_int, [handle_t, C.c_double, C.c_double]),
     "dlra_step_rabug": (C.c_int, [handle_t, C.c_double, C.c_double, C.c_double, C.c_int64, c_int_p, c_int_p]),
     "dlra_step_greedy": (C.c_int, [handle_t, C.c_double, C.c_double]),
+    "dlra_step_greedy_two_factor": (C.c_int, [handle_t, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "dlra_normal_component": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int64,
+                                        c_double_p]),
     "dlra_sync": (C.c_int, [handle_t]),
     "dlra_wait_stream": (C.c_int, [handle_t, C.c_void_p]),
     "dlra_reconstruct_error": (C.c_int, [handle_t, C.c_void_p, C.c_int64, c_double_p]),

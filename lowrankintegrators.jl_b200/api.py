@@ -6,7 +6,8 @@ Same names, argument meaning and error behaviour as the reference:
   ProjectorSplitting(PrimalLieTrotter|DualLieTrotter|Strang)                     src/integrators/projector_splitting.jl:1-41
   UnconventionalAlgorithm                                                        src/integrators/unconventional.jl:13-21
   RankAdaptiveUnconventionalAlgorithm(tol; rmax)                                 src/integrators/rank_adaptive_unconventional.jl:15-23
-  GreedyIntegrator (SVDLike data problems)                                       src/integrators/greedy_integrator.jl:16-22,94-104
+  GreedyIntegrator (SVDLike / TwoFactor data problems, MatrixHybridProblem)      src/integrators/greedy_integrator.jl:16-22,72-104
+  MatrixHybridProblem, normal_component                                          src/primitives.jl:36-41, src/utils.jl:2-20
   SVDLikeRepresentation / TwoFactorRepresentation / truncated_svd                LowRankArithmetic (third party)
 Everything numeric in a step happens inside libdlra.so on the GPU; this file only sequences C-ABI calls.
 User right-hand sides are given in device-evaluable form (rhs.py) instead of Julia closures."""
@@ -66,6 +67,9 @@ class TwoFactorRepresentation:
     @property
     def shape(self):
         return (self.U.shape[0], self.Z.shape[0])
+
+    def copy(self):
+        return TwoFactorRepresentation(self.U, self.Z)
 
 
 def _host(x):
@@ -127,6 +131,16 @@ class MatrixDataProblem:
 
 
 @dataclass
+class MatrixHybridProblem:  # primitives.jl:36-41
+    """y(t) ~ U(t) Z(t)' with dZ/dt = f(Z, U, t).  `f` is a device-evaluable right-hand side F from rhs.py and stands for the
+    Galerkin coefficient dynamics FZ(Z, U, t) = F(U Z')' U (the only form the reference uses, test/data_informed_approximation.jl:75)."""
+    y: object
+    f: object
+    u0: "TwoFactorRepresentation"
+    tspan: tuple
+
+
+@dataclass
 class DLRSolution:
     Y: list
     t: list
@@ -139,15 +153,19 @@ class DLRIntegrator:
         self.t, self.dt, self.sol, self.alg, self.probType, self.iter = t, dt, sol, alg, probType, 0
         self.prob = prob
         self.save_everystep = save_everystep
+        self.two_factor = isinstance(prob.u0, TwoFactorRepresentation)
 
     @property
     def u(self):
-        return SVDLikeRepresentation(*self.cache.get_factors())
+        U, S, V = self.cache.get_factors()
+        if self.two_factor:   # the engine keeps Z in the V slot and S = I
+            return TwoFactorRepresentation(U, V)
+        return SVDLikeRepresentation(U, S, V)
 
     def checkpoint(self):
         """Everything needed to resume (engine state = (U,S,V,r,t,iter) + the data stream position)."""
-        u = self.u
-        return {"U": u.U, "S": u.S, "V": u.V, "t": self.t, "iter": self.iter}
+        U, S, V = self.cache.get_factors()
+        return {"U": U, "S": S, "V": V, "t": self.t, "iter": self.iter}
 
 
 def init_sol(dt, t0, tf, u0):  # primitives.jl:92-104
@@ -223,7 +241,10 @@ class RankAdaptiveUnconventionalAlgorithm:
 
 @dataclass
 class GreedyIntegrator:
-    pass
+    """greedy_integrator.jl:16-22.  Z_alg: sub-stepper of the hybrid Z-flow (default adaptive Tsit5 like the reference);
+    fsal_carry: keep the Z integrator's cached first stage across steps like the reference's never-`set_u!`-ed ZIntegrator."""
+    Z_alg: Optional[SubStepper] = None
+    fsal_carry: bool = True
 
 
 # ------------------------------------------------------------------------------------------------
@@ -255,11 +276,17 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     t0, tf = prob.tspan
     assert tf > t0, "Integration in reverse time direction is not supported"
     u0 = prob.u0
+    two_factor = isinstance(u0, TwoFactorRepresentation)
+    if two_factor and not isinstance(alg, GreedyIntegrator):
+        raise TypeError(f"MethodError: no alg_cache for {type(alg).__name__} with a TwoFactorRepresentation")
+    if isinstance(prob, MatrixHybridProblem) and not (two_factor and isinstance(alg, GreedyIntegrator)):
+        raise TypeError("MethodError: MatrixHybridProblem is solved by the GreedyIntegrator on a TwoFactorRepresentation")
     if resume is not None:   # continue from DLRIntegrator.checkpoint(): factors and time come from the saved state
-        u0 = SVDLikeRepresentation(resume["U"], resume["S"], resume["V"])
+        u0 = (TwoFactorRepresentation(resume["U"], resume["V"]) if two_factor
+              else SVDLikeRepresentation(resume["U"], resume["S"], resume["V"]))
         t0 = resume["t"]
     n, r0 = u0.U.shape
-    m = u0.V.shape[0]
+    m = u0.shape[1]
     adaptive = isinstance(alg, RankAdaptiveUnconventionalAlgorithm)
     rmax = r0
     if adaptive:
@@ -271,10 +298,17 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
         attach_engine(eng)
     elif comm is not None and comm[0] > 1:
         eng.comm_init(*comm)
-    eng.set_factors(u0.U, u0.S, u0.V)  # deepcopy(prob.u0)
+    if two_factor:
+        eng.set_factors(u0.U, np.eye(r0), u0.Z)  # (U, I, Z): the engine keeps Z in the V slot
+    else:
+        eng.set_factors(u0.U, u0.S, u0.V)  # deepcopy(prob.u0)
     if isinstance(prob, MatrixDataProblem):
         y = prob.y
         eng.data_init(y(t0) if callable(y) else y[int(t0 - prob.tspan[0])])  # yprev = y[1] | y(t0) (snapshot at the start time)
+    elif isinstance(prob, MatrixHybridProblem):  # greedy_integrator.jl:41-47: ZIntegrator = init(ODEProblem(f, Z, tspan, U), Z_alg)
+        prob.f.install(eng)
+        sub = alg.Z_alg or SubStepper()
+        eng.set_substepper(L.FLOW_L, _ODE[sub.kind], sub.nsub, sub.abstol, sub.reltol)
     else:
         if isinstance(alg, GreedyIntegrator):
             raise TypeError("MethodError: GreedyIntegrator is defined for data problems")
@@ -330,13 +364,26 @@ def step(integ: DLRIntegrator, alg=None, dt=None):
         r_new, changed = eng.step_rabug(alg.tol, alg.rmax, t, dt)
         if changed:
             print(f"rank adjusted: new rank = {r_new}")  # rank_adaptive_unconventional.jl:230
-    elif isinstance(alg, GreedyIntegrator):
-        eng.data_push(_fetch(y, t, dt))
-        eng.step_greedy(t, dt)
+    elif isinstance(alg, GreedyIntegrator):  # greedy_step! dispatches on (typeof(u), probType), greedy_integrator.jl:72-104
+        eng.data_push(_fetch(integ.prob.y, t, dt))
+        if integ.probType is MatrixHybridProblem:
+            eng.step_greedy_two_factor(L.GREEDY_HYBRID, t, dt, alg.fsal_carry)
+        elif integ.two_factor:
+            eng.step_greedy_two_factor(L.GREEDY_DATA, t, dt)
+        else:
+            eng.step_greedy(t, dt)
     else:
         raise TypeError(f"MethodError: no step! for {type(alg).__name__}")
     integ.t += dt
     integ.iter += 1
+
+
+def normal_component(integ_or_engine, dY, C=None, tol=1e-8, want_matrix=False):
+    """normal_component(LRA, [C,] dY; tol) (utils.jl:2-20) for the factors currently held by the engine: the part of the
+    dynamics dY that the tangent space of the low rank manifold cannot represent (a rank-adaptation indicator).  dY: device
+    n x m matrix.  Returns ‖N‖_F, and N itself as a device matrix when want_matrix."""
+    eng = integ_or_engine.cache if isinstance(integ_or_engine, DLRIntegrator) else integ_or_engine
+    return eng.normal_component(dY, C, tol, want_matrix)
 
 
 def solve(prob, alg, dt=None, **kw) -> DLRSolution:

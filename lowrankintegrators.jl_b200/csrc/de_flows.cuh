@@ -305,7 +305,8 @@ inline void tsit5_stages(dlra_engine* e, FlowRhs& f, int64_t N, const double* u,
     }
 }
 
-inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N, double* X, double t0, double dt) {
+inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N, double* X, double t0, double dt,
+                        FsalCarry* carry = nullptr) {
     DeWork* w = de_work(e);
     Ctx& cx = e->cx;
     w->stages.ensure(10 * N, cx.stream);
@@ -314,17 +315,30 @@ inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N
     double* utmp = w->stages.p + 7 * N;
     double* unew = w->stages.p + 8 * N;
     double* etmp = w->stages.p + 9 * N;
+    // first stage of the first sub-step: evaluated, or (carry) the derivative the previous call ended with
+    auto first_stage = [&](double t) {
+        if (carry && carry->valid && carry->N == N) {
+            DLRA_CUDA(cudaMemcpyAsync(ks[0], carry->k.p, N * sizeof(double), cudaMemcpyDeviceToDevice, cx.stream));
+        } else {
+            f.eval(X, ks[0], t);
+            st.nfev += 1;
+        }
+    };
+    auto keep_stage = [&](const double* k) {
+        carry->k.ensure(N, cx.stream);
+        DLRA_CUDA(cudaMemcpyAsync(carry->k.p, k, N * sizeof(double), cudaMemcpyDeviceToDevice, cx.stream));
+        carry->valid = true; carry->N = N;
+    };
     if (st.ode != DLRA_ODE_TSIT5) {
         const double h = dt / st.nsub;
         double t = t0;
         for (int it = 0; it < st.nsub; ++it) {
+            if (it == 0) first_stage(t);
+            else { f.eval(X, ks[0], t); st.nfev += 1; }
             if (st.ode == DLRA_ODE_EULER) {
-                f.eval(X, ks[0], t);
                 LinComb lc; lc.nk = 1; lc.k[0] = ks[0]; lc.c[0] = h;
                 lincomb(cx, N, X, lc, X);
-                st.nfev += 1;
             } else if (st.ode == DLRA_ODE_RK4) {
-                f.eval(X, ks[0], t);
                 LinComb a; a.nk = 1; a.k[0] = ks[0]; a.c[0] = 0.5 * h;
                 lincomb(cx, N, X, a, utmp);
                 f.eval(utmp, ks[1], t + 0.5 * h);
@@ -338,22 +352,24 @@ inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N
                 b.k[0] = ks[0]; b.k[1] = ks[1]; b.k[2] = ks[2]; b.k[3] = ks[3];
                 b.c[0] = h / 6.0; b.c[1] = h / 3.0; b.c[2] = h / 3.0; b.c[3] = h / 6.0;
                 lincomb(cx, N, X, b, X);
-                st.nfev += 4;
+                st.nfev += 3;
             } else {
-                f.eval(X, ks[0], t);
                 tsit5_stages(e, f, N, X, t, h, ks, utmp, unew);
                 DLRA_CUDA(cudaMemcpyAsync(X, unew, N * sizeof(double), cudaMemcpyDeviceToDevice, cx.stream));
-                st.nfev += 7;
+                st.nfev += 6;
             }
             t += h;
+        }
+        if (carry) {
+            if (st.ode == DLRA_ODE_TSIT5_FIXED) keep_stage(ks[6]);
+            else { f.eval(X, ks[0], t); st.nfev += 1; keep_stage(ks[0]); }
         }
         return;
     }
     // adaptive Tsit5 with the PI controller of SURVEY.md Appendix B
     const double tend = t0 + dt;
     double t = t0;
-    f.eval(X, ks[0], t);   // FSAL invalidated by set_u!
-    st.nfev += 1;
+    first_stage(t);   // FSAL invalidated by set_u! (no carry) or kept (hybrid Z integrator)
     if (st.dt_next <= 0.0) {
         const double d0 = rms_scaled(e, w, N, X, X, X, st.abstol, st.reltol);
         const double d1 = rms_scaled(e, w, N, ks[0], X, X, st.abstol, st.reltol);
@@ -401,6 +417,7 @@ inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N
             st.nreject++;
         }
     }
+    if (carry) keep_stage(ks[0]);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -475,7 +492,7 @@ inline void de_K_flow(dlra_engine* e, double* K, int r, const double* V, double 
     ode_advance(e, e->sub[DLRA_FLOW_K], f, n * (int64_t)r, K, t, dt);
 }
 
-inline void de_L_flow(dlra_engine* e, double* L, int r, const double* U, double t, double dt) {
+inline void de_L_flow(dlra_engine* e, double* L, int r, const double* U, double t, double dt, FsalCarry* carry = nullptr) {
     DeWork* w = de_work(e);
     Ctx& cx = e->cx;
     const RhsCfg& R = e->rhs;
@@ -508,7 +525,7 @@ inline void de_L_flow(dlra_engine* e, double* L, int r, const double* U, double 
     SideFlow f;
     f.e = e; f.w = w; f.rows = m; f.r = r; f.op = &R.B; f.Msm = Au; f.Fc = R.H; f.ldf = R.ldh; f.q = R.q; f.Fsm = Gu;
     f.c_had = chad; f.T = T; f.d1 = nullptr; f.d2 = nullptr; f.s1 = nullptr; f.s2 = nullptr;
-    ode_advance(e, e->sub[DLRA_FLOW_L], f, m * (int64_t)r, L, t, dt);
+    ode_advance(e, e->sub[DLRA_FLOW_L], f, m * (int64_t)r, L, t, dt, carry);
 }
 
 // core flow: S' = sign·( Auu·S + S·Bvv + GH + c·contract(TU, S, S, TV) ),  S: p x q dense

@@ -106,7 +106,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int i = 0; i < 8; ++i) if (h->user_events[i]) cudaEventDestroy(h->user_events[i]);
     de_release(h);
-    h->gws2.release(); h->tws2.release(); h->wtmp2.release();
+    h->gws2.release(); h->tws2.release(); h->wtmp2.release(); h->zcarry.k.release();
     cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     cudaStreamDestroy(h->cx.stream); cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->ax.stream);
@@ -181,6 +181,7 @@ static void set_factors_impl(dlra_handle h, const double* U, int64_t ldu, const 
     DLRA_CUDA(cudaMemcpy2DAsync(h->S, (size_t)h->W * 8, S, lds * 8, (size_t)r * 8, r, kind, s));
     h->r = r;
     h->kl_ready = false;   // a precomputed K/L pass belongs to the factors it was formed with
+    h->zcarry.valid = false;
     if (kind == cudaMemcpyHostToDevice) DLRA_CUDA(cudaStreamSynchronize(s));
 }
 extern "C" int dlra_set_factors_host(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds, const double* V,
@@ -638,6 +639,36 @@ static void greedy_step(dlra_handle h, const Delta& x) {
 }
 
 // ---------------------------------------------------------------------------------------------------
+// greedy step of the two-factor representation u = U*Z' — greedy_integrator.jl:72-92
+// Z lives in the V slot, S stays at identity.
+// ---------------------------------------------------------------------------------------------------
+static void greedy_two_factor_step(dlra_handle h, const Delta& x, int mode, bool carry_fsal, double t, double dt) {
+    Ctx& cx = h->cx;
+    h->kl_ready = false;
+    const int r = h->r;
+    const int64_t n = h->n, m = h->m, W = h->W;
+    double *XZ = h->UB, *Z = h->VB;
+    if (mode == DLRA_GREEDY_DATA) {
+        pass_KL(h, x, r, nullptr, 0, h->U, n, nullptr, 0, Z, m);                              // Z = X'*U (all-reduced)
+    } else {
+        DLRA_REQUIRE(h->comm.nranks == 1, "the hybrid Z-flow is single-GPU (projected operators are not reduced over row shards)");
+        copy_mat(cx, m, r, h->V, m, false, Z, m);
+        if (!carry_fsal) h->zcarry.valid = false;
+        de_L_flow(h, Z, r, h->U, t, dt, &h->zcarry);                                          // dZ/dt = F(U Z')' U
+    }
+    fill_mat(cx, n, r, XZ, n, 0.0, 0.0);
+    pass_KL(h, x, r, Z, m, nullptr, 0, XZ, n, nullptr, 0);                                    // XZ = X*Z
+    // svd(XZ) = (Q_qr*P) * Sigma * Qj'  with  XZ = Q_qr*R,  R = P*Sigma*Qj'   =>   U = Q_qr * (P*Qj')
+    qr_nside(h, XZ, r, h->Rm);
+    h->jws.ensure((int64_t)jacobi_ws_doubles(r), cx.stream);
+    jacobi_svd(cx, r, h->Rm, (int)W, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, 0.0, r, nullptr, nullptr);
+    small_gemm(cx, r, r, r, h->Pm, (int)W, false, h->Qm, (int)W, true, h->T1, (int)W, 1.0, 0.0);
+    gemm_nn(cx, n, r, r, XZ, n, nullptr, 0, h->T1, W, false, h->U, n, 1.0, 0.0);              // mul!(U, Q, P')
+    std::swap(h->V, h->VB);
+    fill_mat(cx, r, r, h->S, W, 0.0, 1.0);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // step entry points
 // ---------------------------------------------------------------------------------------------------
 static StepCtx make_ctx(dlra_handle h, double t, double dt) {
@@ -688,6 +719,17 @@ extern "C" int dlra_step_greedy(dlra_handle h, double t, double dt) {
     DLRA_REQUIRE(!h->rhs.set, "the greedy integrator is defined for data problems");
     Delta x = begin_data_step(h, true);
     greedy_step(h, x);
+    end_data_step(h);
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_step_greedy_two_factor(dlra_handle h, int mode, int carry_fsal, double t, double dt) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(mode == DLRA_GREEDY_DATA || mode == DLRA_GREEDY_HYBRID, "bad greedy mode");
+    if (mode == DLRA_GREEDY_DATA) DLRA_REQUIRE(!h->rhs.set, "DLRA_GREEDY_DATA is defined for data problems");
+    else DLRA_REQUIRE(h->rhs.set, "DLRA_GREEDY_HYBRID needs the right-hand side of the Z-flow (dlra_rhs_set)");
+    Delta x = begin_data_step(h, true);
+    greedy_two_factor_step(h, x, mode, carry_fsal != 0, t, dt);
     end_data_step(h);
     DLRA_API_END(h)
 }
@@ -770,6 +812,7 @@ extern "C" int dlra_rhs_set(dlra_handle h, const dlra_operator* A, const dlra_op
                             const double* H, int64_t ldh, int q, const dlra_operator* D1, const dlra_operator* D2, double c_had) {
     DLRA_API_BEGIN(h)
     de_rhs_set(h, A, B, G, ldg, H, ldh, q, D1, D2, c_had);
+    h->zcarry.valid = false;
     DLRA_API_END(h)
 }
 
@@ -818,6 +861,76 @@ extern "C" int dlra_reconstruct_error(dlra_handle h, const double* Yref, int64_t
     DLRA_CUDA(cudaMemcpyAsync(out, h->scal_dev, 16, cudaMemcpyDeviceToHost, h->cx.stream));
     DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));
     *rel_fro = (out[1] > 0.0) ? sqrt(out[0] / out[1]) : sqrt(out[0]);
+    DLRA_API_END(h)
+}
+
+// C+ = Q * diag(sigma_k > tol ? 1/sigma_k : 0) * P'   for C = P*diag(sigma)*Q'   (pinv(C, atol = tol), utils.jl:7)
+__global__ void __launch_bounds__(256) pinv_from_svd_kernel(int r, const double* __restrict__ P, const double* __restrict__ sigma, const double* __restrict__ Q,
+                                     int ld, double tol, double* __restrict__ Cp) {
+    for (int e = threadIdx.x; e < r * r; e += blockDim.x) {
+        const int i = e % r, j = e / r;
+        double s = 0.0;
+        for (int k = 0; k < r; ++k) {
+            const double sg = sigma[k];
+            if (sg > tol) s = fma(Q[i + (int64_t)k * ld] / sg, P[j + (int64_t)k * ld], s);
+        }
+        Cp[i + (int64_t)j * ld] = s;
+    }
+}
+
+extern "C" int dlra_normal_component(dlra_handle h, const double* dY, int64_t ld, const double* C, int64_t ldc, double tol, double* out,
+                                     int64_t ldo, double* fro_norm) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(dY && ld >= h->n, "bad dY");
+    DLRA_REQUIRE(!out || ldo >= h->n, "bad output leading dimension");
+    DLRA_REQUIRE(!C || ldc >= h->r, "bad C leading dimension");
+    DLRA_REQUIRE(tol >= 0.0, "bad tolerance");
+    Ctx& cx = h->cx;
+    const int r = h->r, r2 = 2 * h->r;
+    const int64_t n = h->n, m = h->m, W = h->W;
+    h->kl_ready = false;                                   // the passes below reuse the pipelined step's partial buffers
+    h->nscr.ensure(n * (int64_t)(3 * r), cx.stream);       // [ U | Kc | Kz ]
+    h->mscr.ensure(m * (int64_t)r2, cx.stream);            // [ L | Z ]
+    double *Xl = h->nscr.p, *Kc = Xl + n * r, *Kz = Xl + 2 * n * r;
+    double *L = h->mscr.p, *Z = L + m * r;
+    gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, Z, m, 1.0, 0.0);                 // Z = V*S'
+    fill_mat(cx, n, r, Kz, n, 0.0, 0.0);
+    Delta d; d.A = dY; d.lda = ld;
+    pass_KL(h, d, r, Z, m, h->U, n, Kz, n, L, m);                                             // Kz = dY*Z ; L = dY'*U (all-reduced)
+    gram_mside(h, main_side(h), r, r, L, Z, h->T1);                                           // T1 = L'*Z = U'*dY*Z
+    if (C) copy_mat(cx, r, r, C, ldc, false, h->Sh, W);
+    else gram_mside(h, main_side(h), r, r, Z, Z, h->Sh);                                      // C = Z'*Z
+    h->jws.ensure((int64_t)jacobi_ws_doubles(r), cx.stream);
+    jacobi_svd(cx, r, h->Sh, (int)W, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, 0.0, r, nullptr, nullptr);
+    pinv_from_svd_kernel<<<1, 256, 0, cx.stream>>>(r, h->Pm, h->sig, h->Qm, (int)W, tol, h->T2);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+    gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->T1, W, false, Kz, n, -1.0, 1.0);             // Kz -= U*(U'*dY*Z)
+    gemm_nn(cx, n, r, r, Kz, n, nullptr, 0, h->T2, W, false, Kc, n, 1.0, 0.0);                // Kc = (I-UU')*dY*Z*C+
+    copy_mat(cx, n, r, h->U, n, false, Xl, n);
+    // N = dY − [U Kc]*[L Z]'
+    if (fro_norm) {
+        dim3 grid((unsigned)cdiv(n, 128), (unsigned)cdiv(m, 512));
+        const int64_t nblocks = (int64_t)grid.x * grid.y;
+        h->gws.ensure(2 * nblocks + 16, cx.stream);
+        recon_err_kernel<<<grid, 128, (size_t)r2 * 8 * sizeof(double), cx.stream>>>(n, m, r2, Xl, n, L, m, dY, ld, h->gws.p);
+        cx.launches++;
+        DLRA_CUDA(cudaGetLastError());
+        sum_pairs_kernel<<<1, 1024, 0, cx.stream>>>(nblocks, h->gws.p, h->scal_dev);
+        cx.launches++;
+        h->comm.allreduce_sum(h->scal_dev, 2, cx);
+    }
+    if (out) {
+        DLRA_CUDA(cudaMemcpy2DAsync(out, (size_t)ldo * sizeof(double), dY, (size_t)ld * sizeof(double), (size_t)n * sizeof(double),
+                                    (size_t)m, cudaMemcpyDeviceToDevice, cx.stream));
+        gemm_nn(cx, n, r2, (int)m, Xl, n, nullptr, 0, L, m, true, out, ldo, -1.0, 1.0);
+    }
+    if (fro_norm) {
+        double res[2];
+        DLRA_CUDA(cudaMemcpyAsync(res, h->scal_dev, 16, cudaMemcpyDeviceToHost, cx.stream));
+        DLRA_CUDA(cudaStreamSynchronize(cx.stream));
+        *fro_norm = sqrt(res[0]);
+    }
     DLRA_API_END(h)
 }
 

@@ -43,6 +43,13 @@ struct SubStepperCfg {
     int64_t nfev = 0, naccept = 0, nreject = 0;
 };
 
+// first stage kept across outer steps by an integrator that is never `set_u!`-ed (hybrid Z-flow, greedy_integrator.jl:72-76)
+struct FsalCarry {
+    DevBuf k;
+    bool valid = false;
+    int64_t N = 0;
+};
+
 struct RhsCfg {
     bool set = false;
     dlra_operator A{}, B{}, D1{}, D2{};
@@ -94,6 +101,7 @@ struct dlra_engine {
     // DE problems
     dlra::RhsCfg rhs;
     dlra::SubStepperCfg sub[3];
+    dlra::FsalCarry zcarry;     // hybrid Z-flow (uses sub[DLRA_FLOW_L])
 
     // profiling of the dominant contraction kernels
     bool time_passes = false;

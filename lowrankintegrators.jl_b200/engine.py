@@ -233,6 +233,9 @@ class Engine:
     def step_greedy(self, t=0.0, dt=1.0):
         self._ck(self.lib.dlra_step_greedy(self.h, float(t), float(dt)))
 
+    def step_greedy_two_factor(self, mode, t=0.0, dt=1.0, carry_fsal=True):
+        self._ck(self.lib.dlra_step_greedy_two_factor(self.h, int(mode), 1 if carry_fsal else 0, float(t), float(dt)))
+
     def sync(self):
         self._ck(self.lib.dlra_sync(self.h))
 
@@ -244,6 +247,21 @@ class Engine:
         out = C.c_double()
         self._ck(self.lib.dlra_reconstruct_error(self.h, p, ld, C.byref(out)))
         return out.value
+
+    def normal_component(self, dY, C_mat=None, tol=1e-8, want_matrix=False):
+        """‖N‖_F (and N as a device matrix when want_matrix) of N = (I-UU') dY (I - Z pinv(C, atol=tol) Z') (utils.jl:2-20)."""
+        p, ld, host, keep = _ptr_ld(dY)
+        assert not host, "normal_component takes a device matrix"
+        pc, ldc = None, 0
+        if C_mat is not None:
+            C_mat = colmajor_device(C_mat)
+            pc, ldc = C_mat.data_ptr(), (C_mat.stride(1) if C_mat.shape[1] > 1 else C_mat.shape[0])
+        out = empty_colmajor(self.n, self.m, torch.device("cuda", self.device)) if want_matrix else None
+        self._after_torch()
+        nrm = C.c_double()
+        self._ck(self.lib.dlra_normal_component(self.h, p, ld, pc, ldc, float(tol), out.data_ptr() if want_matrix else None, self.n,
+                                                C.byref(nrm)))
+        return (nrm.value, out) if want_matrix else nrm.value
 
     def reconstruct(self):
         Y = empty_colmajor(self.n, self.m, torch.device("cuda", self.device))

@@ -131,6 +131,14 @@ class MatrixDataProblem:  # primitives.jl:23-30
 
 
 @dataclass
+class MatrixHybridProblem:  # primitives.jl:36-41
+    y: object      # snapshot function t -> n x m (or a sequence of snapshots)
+    f: Callable    # f(Z, U, t) -> m x r : dZ/dt for the coefficients of y ~ U*Z'
+    u0: object     # TwoFactorRepresentation
+    tspan: tuple
+
+
+@dataclass
 class DLRSolution:  # primitives.jl:46-49
     Y: list
     t: list
@@ -272,36 +280,60 @@ def _tsit5_stages(f, u, t, h, k1):
     return unew, ks
 
 
-def ode_advance(stepper: SubStepper, f, u0, t0, dt):
+def ode_advance(stepper: SubStepper, f, u0, t0, dt, carry: Optional[dict] = None):
     """`set_u!(I, u0); step!(I, dt, true); I.u` (e.g. unconventional.jl:137-139): integrate
     u' = f(u, t) from t0 to exactly t0+dt.  Spec shared verbatim with the CUDA engine
-    (csrc/substep.cuh); adaptive controller per SURVEY.md Appendix B (UNVERIFIED vs OrdinaryDiffEq)."""
+    (csrc/de_flows.cuh); adaptive controller per SURVEY.md Appendix B (UNVERIFIED vs OrdinaryDiffEq).
+
+    carry: None for the K/S/L integrators (their `set_u!` invalidates the cached first stage).  The greedy
+    hybrid step never calls `set_u!` on its ZIntegrator (greedy_integrator.jl:72-76), so OrdinaryDiffEq
+    re-uses the derivative it evaluated at the end of the previous outer step as the first stage -- evaluated
+    with the basis U of *that* step, although `mul!(U, Q, P')` (:81) has changed U in place since.  `carry`
+    (a dict owned by the cache) holds that derivative across calls to reproduce this.  UNVERIFIED against
+    OrdinaryDiffEq like the rest of this function."""
     u = np.array(u0, dtype=np.float64)
     kind = stepper.kind
+
+    def first_stage(t):
+        if carry is not None and carry.get("k") is not None and carry["k"].shape == u.shape:
+            return carry["k"]
+        stepper.nfev += 1
+        return f(u, t)
+
     if kind in ("euler", "rk4", "tsit5_fixed"):
         h = dt / stepper.nsub
         t = t0
-        for _ in range(stepper.nsub):
-            if kind == "euler":
-                u = u + h * f(u, t)
-                stepper.nfev += 1
-            elif kind == "rk4":
+        klast = None
+        for it in range(stepper.nsub):
+            if it == 0:
+                k1 = first_stage(t)
+            else:
                 k1 = f(u, t)
+                stepper.nfev += 1
+            if kind == "euler":
+                u = u + h * k1
+            elif kind == "rk4":
                 k2 = f(u + (0.5 * h) * k1, t + 0.5 * h)
                 k3 = f(u + (0.5 * h) * k2, t + 0.5 * h)
                 k4 = f(u + h * k3, t + h)
                 u = u + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
-                stepper.nfev += 4
+                stepper.nfev += 3
             else:
-                u, _ = _tsit5_stages(f, u, t, h, f(u, t))
-                stepper.nfev += 7
+                u, ks = _tsit5_stages(f, u, t, h, k1)
+                klast = ks[6]
+                stepper.nfev += 6
             t += h
+        if carry is not None:
+            if kind == "tsit5_fixed":
+                carry["k"] = klast
+            else:
+                carry["k"] = f(u, t)
+                stepper.nfev += 1
         return u
     assert kind == "tsit5"
     tend = t0 + dt
     t = t0
-    k1 = f(u, t)  # FSAL invalidated by set_u!
-    stepper.nfev += 1
+    k1 = first_stage(t)  # FSAL invalidated by set_u! (carry is None) or kept (hybrid Z integrator)
     if stepper.dt_next is None:
         # Hairer-Norsett-Wanner initial step heuristic (order 5)
         sk = stepper.abstol + np.abs(u) * stepper.reltol
@@ -340,6 +372,8 @@ def ode_advance(stepper: SubStepper, f, u0, t0, dt):
             q = min(1.0 / qmin, q11 / gamma)
             h = h / q
             stepper.nreject += 1
+    if carry is not None:
+        carry["k"] = k1
     return u
 
 
@@ -398,8 +432,9 @@ class RankAdaptiveUnconventionalAlgorithm:  # rank_adaptive_unconventional.jl:15
 
 
 @dataclass
-class GreedyIntegrator:  # greedy_integrator.jl:16-22 (SVDLike data problems only)
-    pass
+class GreedyIntegrator:  # greedy_integrator.jl:16-22
+    Z_alg: Optional[SubStepper] = None  # sub-stepper of the hybrid Z-flow (default Tsit5(), :19)
+    fsal_carry: bool = True             # keep the Z integrator's cached first stage across outer steps (see ode_advance)
 
 
 def _qr(A):
@@ -418,6 +453,13 @@ def _alg_cache(prob, alg, u, dt, t0):
     (data_integrator.jl:15), for DE problems an explicit RK flow of the projected right-hand side."""
     c = _Cache()
     c.is_data = isinstance(prob, MatrixDataProblem)
+    if isinstance(prob, MatrixHybridProblem):  # greedy_integrator.jl:41-47
+        assert isinstance(alg, GreedyIntegrator), "MethodError: MatrixHybridProblem is solved by the GreedyIntegrator"
+        c.feed = _DataFeed(prob.y, t0)
+        c.f = prob.f
+        c.Z_alg = _stepper(alg.Z_alg)
+        c.Z_carry = {} if alg.fsal_carry else None
+        return c
     if c.is_data:
         c.feed = _DataFeed(prob.y, t0)
         c.dy = None
@@ -533,6 +575,40 @@ def greedy_step(u, c, t, dt):
     u.S[...] = u.U.T @ (X @ u.V)
 
 
+def _polar_factor(XZ):
+    """`Q, _, P = svd(XZ); mul!(U, Q, P')` (greedy_integrator.jl:79-80, 89-90): the orthogonal polar factor."""
+    Q, _, Pt = np.linalg.svd(XZ, full_matrices=False)
+    return Q @ Pt
+
+
+def greedy_step_two_factor(u, c, t, dt):
+    """greedy_integrator.jl:84-92 (TwoFactor, MatrixDataProblem): Z = X'U, then U = polar factor of X*Z."""
+    X = update_data(c.feed.y, t, dt)
+    u.Z[...] = X.T @ u.U
+    u.U[...] = _polar_factor(X @ u.Z)
+
+
+def greedy_step_hybrid(u, c, t, dt):
+    """greedy_integrator.jl:72-82 (MatrixHybridProblem): Z advanced by its own ODE dZ/dt = f(Z, U, t) with
+    the basis U as a (mutated in place) parameter, then U = polar factor of X(t+dt)*Z."""
+    U_now = u.U  # the integrator's parameter p aliases u.U
+    u.Z[...] = ode_advance(c.Z_alg, lambda Z, tt: c.f(Z, U_now, tt), u.Z, t, dt, carry=c.Z_carry)
+    X = update_data(c.feed.y, t, dt)
+    u.U[...] = _polar_factor(X @ u.Z)
+
+
+def normal_component(U, Z, dY, C=None, tol=1e-8):
+    """utils.jl:2-20: (I - U U') dY (I - Z pinv(C, atol=tol) Z'), C = Z'Z unless given.
+    pinv(C; atol) (LinearAlgebra): singular values <= atol are dropped (rtol = 0 when atol > 0)."""
+    if C is None:
+        C = Z.T @ Z
+    P, s, Qt = np.linalg.svd(np.asarray(C, dtype=np.float64))
+    inv = np.where(s > tol, 1.0 / np.where(s > tol, s, 1.0), 0.0)
+    Cp = (Qt.T * inv) @ P.T
+    left = dY - U @ (U.T @ dY)
+    return left - (left @ Z) @ Cp @ Z.T
+
+
 def init(prob, alg, dt) -> DLRIntegrator:
     """projector_splitting.jl:107-115 | unconventional.jl:109-119 | rank_adaptive_unconventional.jl:94-104."""
     t0, tf = prob.tspan
@@ -568,8 +644,13 @@ def step(integ: DLRIntegrator, alg=None, dt=None):
             if not c.is_data:  # ... and the ODE integrators are re-`init`ed (:150-164): fresh controller state
                 for st in (c.K_alg, c.L_alg, c.S_alg):
                     st.dt_next, st.qold = None, 1e-4
-    elif isinstance(alg, GreedyIntegrator):
-        greedy_step(u, c, t, dt)
+    elif isinstance(alg, GreedyIntegrator):  # dispatch of greedy_step! on (typeof(u), probType), greedy_integrator.jl:72-104
+        if integ.probType is MatrixHybridProblem:
+            greedy_step_hybrid(u, c, t, dt)
+        elif isinstance(u, TwoFactorRepresentation):
+            greedy_step_two_factor(u, c, t, dt)
+        else:
+            greedy_step(u, c, t, dt)
     else:
         raise TypeError(f"MethodError: no step! for {type(alg).__name__}")
     integ.t += dt

@@ -40,3 +40,26 @@ def lowrank_stream(n, m, R, seed=0, eps=0.0):
 
 def rel_fro(X, Y):
     return np.linalg.norm(X - Y) / np.linalg.norm(Y)
+
+
+def burgers_truth(n, xi_grid, t_grid, nu=0.005, length=np.pi, substeps=20):
+    """Column-wise Burgers solves standing in for the 100 ODE solves of test/data_informed_approximation.jl:41-64
+    (classical RK4 with `substeps` sub-steps per output interval instead of DifferentialEquations.solve)."""
+    dx = length / n
+    x = (np.arange(n) + 0.5) * dx
+    ub = 0.5 * (np.exp(np.cos(x)) - 1.5) * np.sin(x + 2 * np.pi * 0.37)
+    rho = np.stack([ub + 0.5 * a * np.sin(2 * np.pi * x) + 0.5 * b * np.sin(3 * np.pi * x) for a, b in xi_grid], axis=1)
+
+    def F(r):
+        lap = (np.roll(r, 1, 0) - 2 * r + np.roll(r, -1, 0)) * (nu / dx ** 2)
+        grad = (np.roll(r, -1, 0) - np.roll(r, 1, 0)) * (0.5 / dx)
+        return lap - grad * r
+
+    out = [rho.copy()]
+    for k in range(1, len(t_grid)):
+        h = (t_grid[k] - t_grid[k - 1]) / substeps
+        for _ in range(substeps):
+            k1 = F(rho); k2 = F(rho + 0.5 * h * k1); k3 = F(rho + 0.5 * h * k2); k4 = F(rho + h * k3)
+            rho = rho + (h / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+        out.append(rho.copy())
+    return out, F

@@ -41,6 +41,15 @@ class FakeEngine:
     def step_greedy(self, t=0.0, dt=1.0):
         self.calls.append(("greedy", t, dt))
 
+    def step_greedy_two_factor(self, mode, t=0.0, dt=1.0, carry_fsal=True):
+        self.calls.append(("greedy2", mode, t, dt, carry_fsal))
+
+    def rhs_set(self, *a, **k):
+        self.calls.append(("rhs_set",))
+
+    def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0):
+        self.calls.append(("substepper", flow, ode, nsub))
+
     def sync(self):
         pass
 
@@ -132,3 +141,34 @@ def test_checkpoint_resume_restarts_the_stream_at_the_saved_time(fake):
     assert calls[1] == ("init", 2.0)          # yprev = y[3] (value 2.0), the snapshot at the checkpoint time
     lri.step(integ2)
     assert [c[1] for c in calls if c[0] == "push"][:2] == [3.0, 4.0]
+
+
+def test_greedy_dispatch_on_representation_and_problem_type(fake):
+    # greedy_step! has three methods (greedy_integrator.jl:72-104): (TwoFactor, Hybrid), (TwoFactor, Data), (SVDLike, Data)
+    L = lri._lib
+    y = _snaps(3)
+    u2 = lri.TwoFactorRepresentation(np.eye(6)[:, :2], np.eye(5)[:, :2])
+    sol = lri.solve(lri.MatrixDataProblem(y, u2), lri.GreedyIntegrator())
+    calls = fake.log[0].calls
+    assert calls[0] == ("set_factors", 2)                                     # (U, I, Z)
+    assert [c[:2] for c in calls if c[0] == "greedy2"] == [("greedy2", L.GREEDY_DATA)] * 2
+    assert isinstance(sol.Y[-1], lri.TwoFactorRepresentation)
+    lri.solve(lri.MatrixDataProblem(y, _u0()), lri.GreedyIntegrator())
+    assert [c[0] for c in fake.log[1].calls if c[0].startswith("greedy")] == ["greedy", "greedy"]
+    rhs = lri.LinearRHS(A=1.0)
+    prob = lri.MatrixHybridProblem(lambda t: np.full((6, 5), t), rhs, u2, (0.0, 0.3))
+    lri.solve(prob, lri.GreedyIntegrator(Z_alg=lri.SubStepper("rk4", 2), fsal_carry=False), 0.1)
+    calls = fake.log[2].calls
+    assert ("rhs_set",) in calls and ("substepper", L.FLOW_L, L.ODE_RK4, 2) in calls
+    g = [c for c in calls if c[0] == "greedy2"]
+    assert len(g) == 3 and all(c[1] == L.GREEDY_HYBRID and c[4] is False for c in g)
+    pushes = [c[1] for c in calls if c[0] == "push"]
+    assert np.allclose(pushes, [0.1, 0.2, 0.3])                               # X = y(t + dt) (update_data!, :77)
+
+
+def test_two_factor_needs_the_greedy_integrator(fake):
+    u2 = lri.TwoFactorRepresentation(np.eye(6)[:, :2], np.eye(5)[:, :2])
+    with pytest.raises(TypeError):
+        lri.init(lri.MatrixDataProblem(_snaps(3), u2), lri.UnconventionalAlgorithm(), 1)
+    with pytest.raises(TypeError):
+        lri.init(lri.MatrixHybridProblem(lambda t: np.zeros((6, 5)), lri.LinearRHS(A=1.0), _u0(), (0.0, 1.0)), lri.GreedyIntegrator(), 0.1)

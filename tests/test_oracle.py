@@ -105,3 +105,77 @@ def test_de_problem_linear_matches_exact_flow():
     sol = O.solve(O.MatrixDEProblem(f, X0, (0.0, 0.5)),
                   O.ProjectorSplitting(O.PrimalLieTrotter(), K_alg=rk4, L_alg=rk4, S_alg=rk4), 0.05)
     assert rel_fro(sol.Y[-1].full(), exact) < 1e-8  # KSL is exact on rank-preserving linear flows
+
+
+# ---- greedy integrator on u = U*Z' and the hybrid problem (greedy_integrator.jl:72-92, utils.jl:2-20) ----
+
+def _linear_lowrank_flow(n=60, m=40, r=5, seed=0):
+    from scipy.linalg import expm
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n)); A = 0.3 * (A - A.T)
+    B = rng.standard_normal((m, m)); B = 0.3 * (B - B.T)
+    Y0 = (rng.standard_normal((n, r)) * 2.0 ** -np.arange(r)) @ rng.standard_normal((r, m))
+    y = lambda t: expm(t * A) @ Y0 @ expm(t * B.T)
+    F = lambda X, t: A @ X + X @ B.T
+    U0 = np.linalg.svd(Y0, full_matrices=False)[0][:, :r]
+    return y, F, O.TwoFactorRepresentation(U0, Y0.T @ U0)
+
+
+@pytest.mark.parametrize("carry", [True, False])
+def test_hybrid_greedy_tracks_rank_r_flow(carry):
+    # y(t) has rank r and solves Y' = F(Y): the Galerkin coefficients Z' = F(UZ')'U together with the polar update of U
+    # reproduce it up to the ODE tolerance, with or without the carried first stage
+    y, F, u0 = _linear_lowrank_flow()
+    prob = O.MatrixHybridProblem(y, lambda Z, U, t: F(U @ Z.T, t).T @ U, u0, (0.0, 0.5))
+    sol = O.solve(prob, O.GreedyIntegrator(Z_alg=O.SubStepper("tsit5", abstol=1e-10, reltol=1e-8), fsal_carry=carry), 0.05)
+    assert len(sol.Y) == 11 and isinstance(sol.Y[-1], O.TwoFactorRepresentation)
+    assert rel_fro(sol.Y[-1].full(), y(0.5)) < 1e-6
+    U = sol.Y[-1].U
+    assert np.linalg.norm(U.T @ U - np.eye(U.shape[1])) < 1e-12
+
+
+def test_two_factor_greedy_data_step_is_polar_update():
+    y, _, u0 = _linear_lowrank_flow(seed=3)
+    snaps = [y(0.05 * k) for k in range(4)]
+    integ = O.init(O.MatrixDataProblem(snaps, u0), O.GreedyIntegrator(), 1)
+    Uold = integ.u.U.copy()
+    O.step(integ)
+    X = snaps[1]
+    assert np.allclose(integ.u.Z, X.T @ Uold, atol=1e-14)                    # mul!(Z, X', U)   (:87)
+    G = X @ integ.u.Z
+    Unew = integ.u.U
+    assert np.linalg.norm(Unew.T @ Unew - np.eye(5)) < 1e-12
+    H = Unew.T @ G                                                             # polar factor: U'(XZ) symmetric positive semidefinite
+    assert np.allclose(H, H.T, atol=1e-12) and np.linalg.eigvalsh(0.5 * (H + H.T)).min() > -1e-12
+
+
+def test_normal_component_properties():
+    rng = np.random.default_rng(5)
+    n, m, r = 50, 30, 4
+    U = np.linalg.qr(rng.standard_normal((n, r)))[0]
+    Z = rng.standard_normal((m, r))
+    dY = rng.standard_normal((n, m))
+    N = O.normal_component(U, Z, dY)
+    assert np.linalg.norm(U.T @ N) < 1e-12 and np.linalg.norm(N @ Z) < 1e-12  # orthogonal to range(U) and to range(Z)
+    T = U @ rng.standard_normal((r, m)) + rng.standard_normal((n, r)) @ Z.T   # tangent directions have no normal component
+    assert np.linalg.norm(O.normal_component(U, Z, T)) < 1e-11
+    # rank-deficient Z: pinv(C, atol) drops the null direction instead of blowing up
+    Z2 = Z.copy(); Z2[:, 3] = Z2[:, 2]
+    N2 = O.normal_component(U, Z2, dY)
+    assert np.isfinite(N2).all() and np.linalg.norm(N2 @ Z2) < 1e-10
+
+
+def test_reference_data_informed_burgers_reduced():
+    # test/data_informed_approximation.jl at reduced size (n=128 instead of 1000, 6^2 samples instead of 10^2, rank 10, and
+    # viscosity 0.02 instead of 0.005 so that the coarser grid resolves the front): <= 10 % error
+    from tests.problems import burgers_truth
+    n, mm, r, dt = 128, 6, 10, 1e-2
+    xi = [(a, b) for b in np.linspace(-1, 1, mm) for a in np.linspace(-1, 1, mm)]
+    t_grid = np.arange(0, 0.3 + 1e-12, dt)
+    truth, F = burgers_truth(n, xi, t_grid, nu=0.02)
+    U0 = O.truncated_svd(np.hstack([truth[0], truth[1]]), r).U               # :67-69
+    u0 = O.TwoFactorRepresentation(U0, truth[0].T @ U0)
+    y = lambda t: truth[min(int(np.floor(t / dt + 1e-9)), len(t_grid) - 1)]    # interpolate_data (:70-73)
+    prob = O.MatrixHybridProblem(y, lambda Z, U, t: F(U @ Z.T).T @ U, u0, (0.0, 0.3))
+    sol = O.solve(prob, O.GreedyIntegrator(), dt)
+    assert rel_fro(sol.Y[-1].full(), truth[-1]) <= 0.1

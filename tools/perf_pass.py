@@ -21,7 +21,7 @@ def main():
     S0 = torch.diag(torch.tensor([2.0 ** -i for i in range(r)], device=dev, dtype=torch.float64))
     for alg in algs:
         for kind, kname in ((L.DATA_DELTA, "delta"), (L.DATA_SNAPSHOT, "snapshot")):
-            if alg == "greedy" and kind == L.DATA_DELTA: continue
+            if alg in ("greedy", "greedy2", "normal") and kind == L.DATA_DELTA: continue
             if kname not in kinds: continue
             eng = lri.Engine(n, m, r, rmax=r, rank_adaptive=(alg == "rabug"))
             eng.set_factors(U0, S0, V0)
@@ -29,10 +29,13 @@ def main():
             look = len(sys.argv) > 7 and sys.argv[7] == "lookahead" and alg == "bug" and kind == L.DATA_SNAPSHOT
             if look: eng.data_push(snaps[1], kind)
             def one(i):
+                if alg == "normal":
+                    eng.normal_component(snaps[i % 3]); return
                 eng.data_push(snaps[(i + 2) % 3] if look else snaps[(i + 1) % 3], kind)
                 if alg == "bug": eng.step_bug()
                 elif alg == "ksl": eng.step_ksl(L.KSL_PRIMAL)
                 elif alg == "rabug": eng.step_rabug(1e-3, r)
+                elif alg == "greedy2": eng.step_greedy_two_factor(L.GREEDY_DATA)
                 else: eng.step_greedy()
             for i in range(3): one(i)
             eng.sync(); eng.set_profiling(True); eng.stats(reset=True)
