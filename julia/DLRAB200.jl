@@ -1,7 +1,8 @@
 # DLRAB200.jl — the `ccall` binding a LowRankIntegrators.jl maintainer would add to route the per-step DLRA hot path
 # through libdlra.so (include/dlra.h).  It keeps the package's API surface: MatrixDEProblem / MatrixDataProblem,
 # `LowRankIntegrators.solve(prob, alg, dt)`, ProjectorSplitting / UnconventionalAlgorithm /
-# RankAdaptiveUnconventionalAlgorithm and SVDLikeRepresentation factors; only `alg_cache` and `step!` change.
+# RankAdaptiveUnconventionalAlgorithm / GreedyIntegrator (also on TwoFactorRepresentation and MatrixHybridProblem) and the
+# SVDLikeRepresentation factors; only `alg_cache` and `step!` change.
 #
 # NOT EXECUTED IN THIS REPOSITORY'S CI: Julia is not installed in the build image (SURVEY.md F2); the same C symbols are
 # exercised through ctypes by lowrankintegrators.jl_b200/_lib.py and the tests.  No CUDA.jl kernels, no CPU fallback.
@@ -16,9 +17,9 @@ module DLRAB200
 
 using LowRankIntegrators, LowRankArithmetic, LinearAlgebra
 import LowRankIntegrators: alg_cache, step!, init, update_sol!, init_sol, DLRIntegrator, DLRSolution,
-                           MatrixDataProblem, MatrixDEProblem, AbstractDLRAlgorithm, AbstractDLRAlgorithm_Cache,
-                           ProjectorSplitting, PrimalLieTrotter, DualLieTrotter, Strang,
-                           UnconventionalAlgorithm, RankAdaptiveUnconventionalAlgorithm
+                           MatrixDataProblem, MatrixDEProblem, MatrixHybridProblem, AbstractDLRAlgorithm,
+                           AbstractDLRAlgorithm_Cache, ProjectorSplitting, PrimalLieTrotter, DualLieTrotter, Strang,
+                           UnconventionalAlgorithm, RankAdaptiveUnconventionalAlgorithm, GreedyIntegrator
 
 const libdlra = get(ENV, "LIBDLRA", "libdlra.so")
 const Handle = Ptr{Cvoid}
@@ -27,6 +28,7 @@ const DLRA_RANK_ADAPTIVE = Cint(1)
 const KSL_PRIMAL, KSL_DUAL, KSL_STRANG = Cint(0), Cint(1), Cint(2)
 const DATA_SNAPSHOT, DATA_DELTA = Cint(0), Cint(1)
 const FLOW_K, FLOW_S, FLOW_L = Cint(0), Cint(1), Cint(2)
+const GREEDY_DATA, GREEDY_HYBRID = Cint(0), Cint(1)
 const ODE_EULER, ODE_RK4, ODE_TSIT5_FIXED, ODE_TSIT5 = Cint(0), Cint(1), Cint(2), Cint(3)
 const OP_NONE, OP_DENSE, OP_CSR, OP_IDENTITY_SCALED = Cint(0), Cint(1), Cint(2), Cint(3)
 
@@ -85,6 +87,7 @@ mutable struct B200Cache <: AbstractDLRAlgorithm_Cache
     m::Int
     pushed::Int  # snapshots already handed to the engine beyond the current time (0, 1 or 2: one snapshot of lookahead)
     tf           # end of the time span (no lookahead past it)
+    two_factor::Bool  # u = U*Z': the engine keeps Z in the V slot and S = I
 end
 
 function B200Cache(device, n, m, r0, rmax, adaptive::Bool)
@@ -92,7 +95,7 @@ function B200Cache(device, n, m, r0, rmax, adaptive::Bool)
     rc = ccall((:dlra_create, libdlra), Cint, (Cint, Int64, Int64, Cint, Cint, Cint, Ref{Handle}),
                device, n, m, r0, rmax, adaptive ? DLRA_RANK_ADAPTIVE : Cint(0), href)
     rc == 0 || throw(DLRAError(rc, unsafe_string(ccall((:dlra_last_error, libdlra), Cstring, (Handle,), C_NULL))))
-    c = B200Cache(href[], nothing, n, m, 0, nothing)
+    c = B200Cache(href[], nothing, n, m, 0, nothing, false)
     finalizer(x -> ccall((:dlra_destroy, libdlra), Cint, (Handle,), x.h), c)
     return c
 end
@@ -102,6 +105,14 @@ set_factors!(c::B200Cache, u::SVDLikeRepresentation) =
                      (Handle, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Cint),
                      c.h, u.U, size(u.U, 1), u.S, size(u.S, 1), u.V, size(u.V, 1), rank(u)))
 
+function set_factors!(c::B200Cache, u::TwoFactorRepresentation)
+    r = size(u.U, 2)
+    c.two_factor = true
+    check(c.h, ccall((:dlra_set_factors_host, libdlra), Cint,
+                     (Handle, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Cint),
+                     c.h, u.U, size(u.U, 1), Matrix{Float64}(I, r, r), r, u.Z, size(u.Z, 1), r))
+end
+
 "update_sol! (primitives.jl:82-90): deep copy of the device factors into a fresh SVDLikeRepresentation"
 function get_factors(c::B200Cache)
     r = Ref{Cint}(0)
@@ -110,7 +121,7 @@ function get_factors(c::B200Cache)
     check(c.h, ccall((:dlra_get_factors_host, libdlra), Cint,
                      (Handle, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Cint}),
                      c.h, U, c.n, S, r[], V, c.m, r))
-    return SVDLikeRepresentation(U, S, V)
+    return c.two_factor ? TwoFactorRepresentation(U, V) : SVDLikeRepresentation(U, S, V)
 end
 
 ode_code(alg) = alg isa Tsit5 ? ODE_TSIT5 : alg isa RK4 ? ODE_RK4 : alg isa Euler ? ODE_EULER :
@@ -118,7 +129,7 @@ ode_code(alg) = alg isa Tsit5 ? ODE_TSIT5 : alg isa RK4 ? ODE_RK4 : alg isa Eule
 
 # ---- alg_cache ---------------------------------------------------------------------------------------------------
 function alg_cache(prob::MatrixDataProblem, w::OnB200, u, dt; t0 = prob.tspan[1])
-    n, r = size(u.U); m = size(u.V, 1)
+    n, r = size(u.U); m = size(u, 2)
     adaptive = w.alg isa RankAdaptiveUnconventionalAlgorithm
     rmax = adaptive ? Int(min(w.alg.alg_params.r_max, 128, m ÷ 2)) : r
     c = B200Cache(w.device, n, m, r, max(rmax, r), adaptive)
@@ -147,6 +158,39 @@ function alg_cache(prob::MatrixDEProblem{<:FactoredRHS}, w::OnB200, u, dt; t0 = 
                          c.h, flow, ode_code(a), Cint(get(kw, :nsub, 1)), get(kw, :abstol, 1e-6), get(kw, :reltol, 1e-3)))
     end
     return c
+end
+
+# greedy_integrator.jl:41-47: the Z-flow dZ/dt = F(U Z')' U (FZ of test/data_informed_approximation.jl:75) runs on the device
+function alg_cache(prob::MatrixHybridProblem{<:Any,<:FactoredRHS}, w::OnB200{<:GreedyIntegrator}, u::TwoFactorRepresentation, dt;
+                   t0 = prob.tspan[1])
+    n, r = size(u.U); m = size(u.Z, 1)
+    c = B200Cache(w.device, n, m, r, r, false)
+    set_factors!(c, u)
+    c.y = prob.y
+    c.tf = prob.tspan[2]
+    f = prob.f
+    check(c.h, ccall((:dlra_rhs_set, libdlra), Cint,
+                     (Handle, Ref{Operator}, Ref{Operator}, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Cint,
+                      Ref{Operator}, Ref{Operator}, Float64),
+                     c.h, f.A, f.B, f.G, f.ldg, f.H, f.ldh, f.q, f.D1, f.D2, f.c_had))
+    p = w.alg.alg_params
+    check(c.h, ccall((:dlra_set_substepper, libdlra), Cint, (Handle, Cint, Cint, Cint, Float64, Float64),
+                     c.h, FLOW_L, ode_code(p.Z_alg), Cint(get(p.Z_kwargs, :nsub, 1)), get(p.Z_kwargs, :abstol, 1e-6),
+                     get(p.Z_kwargs, :reltol, 1e-3)))
+    return c
+end
+
+"""
+    normal_component(cache, dY_device, ld; tol = 1e-8) -> ‖(I-UU')·dY·(I-Z·pinv(Z'Z, atol=tol)·Z')‖_F
+
+utils.jl:2-20 for the factors held by the engine (dY: device pointer to the n_local x m dynamics, e.g. a CuArray).
+"""
+function normal_component(c::B200Cache, dY::Ptr{Float64}, ld::Integer; tol = 1e-8)
+    nrm = Ref{Float64}(0.0)
+    check(c.h, ccall((:dlra_normal_component, libdlra), Cint,
+                     (Handle, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Int64, Ref{Float64}),
+                     c.h, dY, ld, C_NULL, 0, tol, C_NULL, 0, nrm))
+    return nrm[]
 end
 
 function init(prob, w::OnB200, dt)
@@ -199,6 +243,17 @@ function step!(integrator::DLRIntegrator, w::OnB200, dt)
         check(c.h, ccall((:dlra_step_rabug, libdlra), Cint, (Handle, Float64, Float64, Float64, Int64, Ref{Cint}, Ref{Cint}),
                          c.h, t, dt, alg.alg_params.tol, min(alg.alg_params.r_max, typemax(Int64)), rnew, changed))
         changed[] != 0 && println("rank adjusted: new rank = $(rnew[])")   # rank_adaptive_unconventional.jl:230
+    elseif alg isa GreedyIntegrator                                         # greedy_step! methods, greedy_integrator.jl:72-104
+        push_data!(c, t, dt)                                                # X = y(t+dt) | y[t+dt]
+        if integrator.probType <: MatrixHybridProblem
+            check(c.h, ccall((:dlra_step_greedy_two_factor, libdlra), Cint, (Handle, Cint, Cint, Float64, Float64),
+                             c.h, GREEDY_HYBRID, Cint(1), t, dt))
+        elseif c.two_factor
+            check(c.h, ccall((:dlra_step_greedy_two_factor, libdlra), Cint, (Handle, Cint, Cint, Float64, Float64),
+                             c.h, GREEDY_DATA, Cint(1), t, dt))
+        else
+            check(c.h, ccall((:dlra_step_greedy, libdlra), Cint, (Handle, Float64, Float64), c.h, t, dt))
+        end
     else
         throw(MethodError(step!, (integrator, w, dt)))
     end
