@@ -20,7 +20,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures = []
     for (n, m, r, name) in [(4096, 512, 8, "bug"), (4096, 512, 8, "ksl_primal"), (4096, 512, 8, "ksl_dual"), (6144, 384, 16, "bug"),
-                            (4096, 512, 6, "rabug"), (4096, 512, 8, "greedy"), (2050, 130, 5, "bug")]:
+                            (4096, 512, 6, "rabug"), (4096, 512, 8, "greedy"), (2050, 130, 5, "bug"),
+                            (4096, 512, 8, "greedy2"), (2050, 130, 5, "greedy2")]:
         A = lowrank_stream(n, m, 2 * r if name != "rabug" else 10, seed=21, eps=0.0 if name == "rabug" else 1e-4)
         snaps = [A(0.04 * k) for k in range(4)]
         X0 = O.truncated_svd(snaps[0], r)
@@ -31,10 +32,16 @@ def main():
             "ksl_dual": (lri.ProjectorSplitting(lri.DualLieTrotter()), O.ProjectorSplitting(O.DualLieTrotter())),
             "rabug": (lri.RankAdaptiveUnconventionalAlgorithm(1e-6, rmax=16), O.RankAdaptiveUnconventionalAlgorithm(1e-6, rmax=16)),
             "greedy": (lri.GreedyIntegrator(), O.GreedyIntegrator()),
+            "greedy2": (lri.GreedyIntegrator(), O.GreedyIntegrator()),
         }[name]
         dsn = [torch.from_numpy(np.ascontiguousarray(s[lo:hi].T)).cuda().t() for s in snaps]
-        gint = lri.init(lri.MatrixDataProblem(dsn, lri.SVDLikeRepresentation(X0.U[lo:hi], X0.S, X0.V)), galg, 1, comm="torch")
-        oint = O.init(O.MatrixDataProblem(snaps, X0), oalg, 1)
+        if name == "greedy2":   # u = U*Z' (greedy_integrator.jl:84-92): U row-sharded, Z replicated
+            Z0 = snaps[0].T @ X0.U
+            gu0, ou0 = lri.TwoFactorRepresentation(X0.U[lo:hi], Z0), O.TwoFactorRepresentation(X0.U, Z0)
+        else:
+            gu0, ou0 = lri.SVDLikeRepresentation(X0.U[lo:hi], X0.S, X0.V), X0
+        gint = lri.init(lri.MatrixDataProblem(dsn, gu0), galg, 1, comm="torch")
+        oint = O.init(O.MatrixDataProblem(snaps, ou0), oalg, 1)
         for k in range(3):
             O.step(oint)
             lri.step(gint)
@@ -45,7 +52,8 @@ def main():
             if rank == 0:
                 ou = oint.u
                 ok_rank = gu.rank == ou.rank
-                err = rel_fro(Ufull @ gu.S @ gu.V.T, ou.full()) if ok_rank else np.inf
+                full = Ufull @ gu.Z.T if name == "greedy2" else Ufull @ gu.S @ gu.V.T
+                err = rel_fro(full, ou.full()) if ok_rank else np.inf
                 orth = np.linalg.norm(Ufull.T @ Ufull - np.eye(gu.rank))
                 if not (ok_rank and err <= 1e-10 and orth < 1e-12):
                     failures.append((n, m, r, name, k, gu.rank, ou.rank, err, orth))
