@@ -55,6 +55,14 @@ def sharded_ksl_step(U, S, V, dA):
     return U1, RL.T, V1
 
 
+def sharded_greedy_two_factor_step(U, Z, X):
+    """greedy_integrator.jl:84-92 as the engine runs it: Z all-reduced, polar factor via TSQR + SVD of the small R."""
+    Z1 = allreduce(X.T @ U)
+    Q, R = dist_tsqr(X @ Z1)
+    P, _, Qt = np.linalg.svd(R)
+    return Q @ (P @ Qt), Z1
+
+
 def main():
     dist.init_process_group("gloo")
     world, rank = dist.get_world_size(), dist.get_rank()
@@ -77,6 +85,15 @@ def main():
             dist.all_gather_object(parts, U)
             err = rel_fro(np.vstack(parts) @ S @ V.T, oint.u.full())
             ok = ok and err < 1e-11
+    U = X0.U[lo:hi].copy()
+    Z = snaps[0].T @ X0.U
+    oint = O.init(O.MatrixDataProblem(snaps, O.TwoFactorRepresentation(X0.U, Z)), O.GreedyIntegrator(), 1)
+    for k in range(3):
+        U, Z = sharded_greedy_two_factor_step(U, Z, snaps[k + 1][lo:hi])
+        O.step(oint)
+        parts = [None] * world
+        dist.all_gather_object(parts, U)
+        ok = ok and rel_fro(np.vstack(parts) @ Z.T, oint.u.full()) < 1e-11
     flag = torch.tensor([1 if ok else 0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
