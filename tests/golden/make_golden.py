@@ -45,6 +45,23 @@ def main():
                       "ksl_strang": O.ProjectorSplitting(O.Strang(), K_alg=rk4, L_alg=rk4, S_alg=rk4)}.items():
         sol = O.solve(O.MatrixDEProblem(f, Z0, (0.0, 0.04)), alg, 0.01)
         out[f"de_{name}_Y"] = np.stack([y.full() for y in sol.Y])
+    # greedy steps on u = U*Z' (greedy_integrator.jl:72-92): data problem on the snapshots above, hybrid problem on the linear flow
+    Zs = snaps[0].T @ X0.U
+    sol = O.solve(O.MatrixDataProblem(snaps, O.TwoFactorRepresentation(X0.U, Zs)), O.GreedyIntegrator())
+    out["data_greedy2_Y"] = np.stack([y.full() for y in sol.Y])
+    from scipy.linalg import expm
+    # the data rotate with the *other* generator, so that the basis update does not commute with the projected operator
+    # U'AU of the Z-flow (otherwise the carried first stage and a fresh one coincide to round-off)
+    Y0 = Z0.full()
+    yfun = lambda t: expm(3.0 * t * W2) @ Y0 @ expm(3.0 * t * W1)
+    fz = lambda Z, U, t: f(U @ Z.T, t).T @ U
+    for carry in (True, False):
+        alg = O.GreedyIntegrator(Z_alg=O.SubStepper("rk4", nsub=2), fsal_carry=carry)
+        sol = O.solve(O.MatrixHybridProblem(yfun, fz, O.TwoFactorRepresentation(Z0.U, Y0.T @ Z0.U), (0.0, 0.04)), alg, 0.01)
+        out[f"hybrid_carry{int(carry)}_Y"] = np.stack([y.full() for y in sol.Y])
+        # for this linear F the carried stage only rotates Z (and U with it): U*Z' moves by 1e-10, Z itself by 1e-5
+        out[f"hybrid_carry{int(carry)}_Z"] = np.stack([y.Z for y in sol.Y])
+    out["hybrid_snaps"] = np.stack([yfun(0.01 * k) for k in range(5)])
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "oracle_golden.npz"), **out)
     print({k: v.shape for k, v in out.items()})
 

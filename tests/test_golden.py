@@ -26,6 +26,49 @@ def test_oracle_reproduces_golden_data_problem(name):
     assert max(rel(y.full(), g) for y, g in zip(sol.Y, G[f"data_{name}_Y"])) < 1e-12
 
 
+def _hybrid_inputs():
+    snaps = G["hybrid_snaps"]
+    y = lambda t: snaps[min(int(round(t / 0.01)), len(snaps) - 1)]
+    U0 = G["de_U0"]
+    Y0 = U0 @ G["de_S0"] @ G["de_V0"].T
+    return y, U0, Y0.T @ U0
+
+
+def test_oracle_reproduces_golden_two_factor_and_hybrid():
+    from oracle import dlra_oracle as O
+    Z0 = G["data_snaps"][0].T @ G["data_U0"]
+    sol = O.solve(O.MatrixDataProblem(list(G["data_snaps"]), O.TwoFactorRepresentation(G["data_U0"], Z0)), O.GreedyIntegrator())
+    assert max(rel(y.full(), g) for y, g in zip(sol.Y, G["data_greedy2_Y"])) < 1e-12
+    W1, W2 = G["de_W1"], G["de_W2"]
+    fz = lambda Z, U, t: (W1 @ (U @ Z.T) + U @ Z.T + (U @ Z.T) @ W2).T @ U
+    y, U0, Zh = _hybrid_inputs()
+    for carry in (True, False):
+        alg = O.GreedyIntegrator(Z_alg=O.SubStepper("rk4", nsub=2), fsal_carry=carry)
+        sol = O.solve(O.MatrixHybridProblem(y, fz, O.TwoFactorRepresentation(U0, Zh), (0.0, 0.04)), alg, 0.01)
+        assert max(rel(s.full(), g) for s, g in zip(sol.Y, G[f"hybrid_carry{int(carry)}_Y"])) < 1e-12
+        assert max(rel(s.Z, g) for s, g in zip(sol.Y, G[f"hybrid_carry{int(carry)}_Z"])) < 1e-11
+    assert rel(G["hybrid_carry1_Z"][-1], G["hybrid_carry0_Z"][-1]) > 1e-6   # the fixtures do tell the two variants apart
+
+
+@pytest.mark.gpu
+def test_engine_matches_golden_two_factor_and_hybrid():
+    import torch
+    import lowrankintegrators.jl_b200 as lri
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(np.asarray(x).T)).cuda().t()
+    Z0 = G["data_snaps"][0].T @ G["data_U0"]
+    sol = lri.solve(lri.MatrixDataProblem(list(G["data_snaps"]), lri.TwoFactorRepresentation(G["data_U0"], Z0)), lri.GreedyIntegrator())
+    assert max(rel(y.full(), g) for y, g in zip(sol.Y, G["data_greedy2_Y"])) <= 1e-10
+    N = G["de_W1"].shape[0]
+    y, U0, Zh = _hybrid_inputs()
+    for carry in (True, False):
+        rhs = lri.LinearRHS(A=dev(G["de_W1"] + np.eye(N)), B=dev(G["de_W2"].T))
+        alg = lri.GreedyIntegrator(Z_alg=lri.SubStepper("rk4", nsub=2), fsal_carry=carry)
+        sol = lri.solve(lri.MatrixHybridProblem(y, rhs, lri.TwoFactorRepresentation(U0, Zh), (0.0, 0.04)), alg, 0.01)
+        assert len(sol.Y) == 5
+        assert max(rel(s.full(), g) for s, g in zip(sol.Y, G[f"hybrid_carry{int(carry)}_Y"])) <= 1e-10
+        assert max(rel(s.Z, g) for s, g in zip(sol.Y, G[f"hybrid_carry{int(carry)}_Z"])) <= 1e-9
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", DATA_ALGS)
 def test_engine_matches_golden_data_problem(name):

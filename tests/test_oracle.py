@@ -179,3 +179,56 @@ def test_reference_data_informed_burgers_reduced():
     prob = O.MatrixHybridProblem(y, lambda Z, U, t: F(U @ Z.T).T @ U, u0, (0.0, 0.3))
     sol = O.solve(prob, O.GreedyIntegrator(), dt)
     assert rel_fro(sol.Y[-1].full(), truth[-1]) <= 0.1
+
+
+# ---- sub-steppers: the restated Tsit5 tableau against its published properties (OrdinaryDiffEq itself is not available) ----
+
+def test_tsit5_tableau_consistency():
+    A, c, bt = O.TSIT5_A, O.TSIT5_C, O.TSIT5_BTILDE
+    for s in range(1, 7):
+        assert abs(sum(A[s]) - c[s]) < 1e-14                      # row sums = nodes
+    b = np.array(list(A[6]) + [0.0])                               # FSAL: the 7th stage row is the 5th-order weight vector
+    cc = np.array(c)
+    Am = np.zeros((7, 7))
+    for s in range(1, 7):
+        Am[s, :len(A[s])] = A[s]
+    # order conditions up to order 4 (all of them) and the quadrature conditions of order 5
+    assert abs(b.sum() - 1) < 1e-14 and abs(b @ cc - 1 / 2) < 1e-14 and abs(b @ cc ** 2 - 1 / 3) < 1e-14
+    assert abs(b @ (Am @ cc) - 1 / 6) < 1e-14 and abs(b @ cc ** 3 - 1 / 4) < 1e-14
+    assert abs(b @ (cc * (Am @ cc)) - 1 / 8) < 1e-14 and abs(b @ (Am @ cc ** 2) - 1 / 12) < 1e-14
+    assert abs(b @ (Am @ (Am @ cc)) - 1 / 24) < 1e-14 and abs(b @ cc ** 4 - 1 / 5) < 1e-13
+    bt = np.array(bt)
+    assert abs(bt.sum()) < 1e-14                                   # error weights: difference of two consistent methods
+    bhat = b - bt                                                  # embedded 4th-order solution
+    assert abs(bhat @ cc - 1 / 2) < 1e-14 and abs(bhat @ cc ** 2 - 1 / 3) < 1e-14 and abs(bhat @ cc ** 3 - 1 / 4) < 1e-13
+
+
+@pytest.mark.parametrize("kind,order", [("euler", 1), ("rk4", 4), ("tsit5_fixed", 5)])
+def test_fixed_substeppers_converge_with_their_order(kind, order):
+    rng = np.random.default_rng(2)
+    M = rng.standard_normal((4, 4)); M = 0.5 * (M - M.T) - 0.1 * np.eye(4)
+    f = lambda u, t: M @ u + np.sin(3 * t) * np.ones((4, 1)) * 0.3 + 0.2 * u * u       # nonlinear, non-autonomous
+    u0 = rng.standard_normal((4, 1))
+    ref = O.ode_advance(O.SubStepper("tsit5_fixed", nsub=2000), f, u0, 0.0, 1.0)
+    errs = [np.linalg.norm(O.ode_advance(O.SubStepper(kind, nsub=ns), f, u0, 0.0, 1.0) - ref) for ns in (20, 40)]
+    assert abs(np.log2(errs[0] / errs[1]) - order) < 0.35, errs
+
+
+def test_adaptive_tsit5_meets_tolerance_and_reaches_the_end_exactly():
+    from scipy.integrate import solve_ivp
+    rng = np.random.default_rng(3)
+    M = rng.standard_normal((6, 6)); M = M - M.T
+    f = lambda u, t: M @ u - 0.5 * u ** 3
+    u0 = rng.standard_normal(6)
+    exact = solve_ivp(lambda t, u: f(u, t), (0.0, 2.0), u0, rtol=1e-12, atol=1e-14, method="DOP853").y[:, -1]
+    prev = None
+    for tol in (1e-4, 1e-6, 1e-8):
+        st = O.SubStepper("tsit5", abstol=tol * 1e-3, reltol=tol)
+        u = u0.copy()
+        for k in range(4):                                        # four outer steps: the controller state carries over
+            u = O.ode_advance(st, f, u, 0.5 * k, 0.5)
+        err = np.linalg.norm(u - exact) / np.linalg.norm(exact)
+        assert err < 50 * tol, (tol, err)
+        assert prev is None or st.naccept > prev                  # tighter tolerance -> more steps
+        assert st.nreject <= st.naccept
+        prev = st.naccept
