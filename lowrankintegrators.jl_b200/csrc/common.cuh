@@ -31,6 +31,17 @@ struct CudaError : std::runtime_error {
         if (!(cond)) throw ::dlra::CudaError(1, std::string(msg) + " [" #cond "]");                \
     } while (0)
 
+// cudaFuncSetAttribute is per device: a host process that drives several GPUs (one handle each) must repeat it on each one.
+// `mask` is a function-local static; returns true the first time the calling kernel wrapper runs on the current device.
+static inline bool first_use_on_this_device(unsigned long long& mask) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+}
+
 static inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return cdiv(a, b) * b; }
 

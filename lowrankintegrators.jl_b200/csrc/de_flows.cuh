@@ -15,6 +15,7 @@
 // The explicit RK schemes (Euler, RK4, Tsit5 fixed/adaptive) restate oracle/dlra_oracle.py::ode_advance 1:1.
 #pragma once
 #include "engine.cuh"
+#include <mutex>
 
 namespace dlra {
 
@@ -192,7 +193,13 @@ static std::vector<std::pair<dlra_engine*, DeWork*>>& de_registry() {
     static std::vector<std::pair<dlra_engine*, DeWork*>> r;
     return r;
 }
+// handles may be driven from different host threads (one handle per thread): the registry itself is shared
+static std::mutex& de_registry_mutex() {
+    static std::mutex mu;
+    return mu;
+}
 inline DeWork* de_work(dlra_engine* e) {
+    std::lock_guard<std::mutex> lock(de_registry_mutex());
     for (auto& pr : de_registry()) if (pr.first == e) return pr.second;
     DeWork* w = new DeWork();
     DLRA_CUDA(cudaHostAlloc(&w->scal_host, 4 * sizeof(double), cudaHostAllocDefault));
@@ -200,6 +207,7 @@ inline DeWork* de_work(dlra_engine* e) {
     return w;
 }
 inline void de_release(dlra_engine* e) {
+    std::lock_guard<std::mutex> lock(de_registry_mutex());
     auto& reg = de_registry();
     for (size_t i = 0; i < reg.size(); ++i)
         if (reg[i].first == e) {

@@ -29,6 +29,8 @@ extern "C" const char* dlra_version(void) { return "dlra-b200 0.1 (sm_100a)"; }
 
 extern "C" const char* dlra_last_error(dlra_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
+extern "C" int dlra_destroy(dlra_handle h);
+
 extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int rmax, int flags, dlra_handle* out) {
     if (!out) { g_create_error = "out == NULL"; return DLRA_EINVAL; }
     *out = nullptr;
@@ -85,8 +87,12 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
     } catch (const CudaError& ex) {
         g_create_error = ex.what();
         int code = ex.code;
-        delete e;
+        dlra_destroy(e);   // releases whatever was allocated before the failure
         return code;
+    } catch (const std::exception& ex) {
+        g_create_error = ex.what();
+        dlra_destroy(e);
+        return DLRA_ECUDA;
     }
     *out = e;
     return DLRA_OK;
@@ -95,21 +101,29 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
 extern "C" int dlra_destroy(dlra_handle h) {
     if (!h) return DLRA_OK;
     cudaSetDevice(h->device);
-    cudaStreamSynchronize(h->cx.stream);
-    cudaStreamSynchronize(h->ax.stream);
-    cudaStreamSynchronize(h->copy_stream);
+    if (h->cx.stream) cudaStreamSynchronize(h->cx.stream);
+    if (h->ax.stream) cudaStreamSynchronize(h->ax.stream);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     h->comm.destroy();
     cudaFree(h->U); cudaFree(h->UB); cudaFree(h->V); cudaFree(h->VB); cudaFree(h->small_block);
     cudaFree(h->r_new_dev); cudaFreeHost(h->r_new_host); cudaFree(h->cx.counters);
-    for (int i = 0; i < dlra_engine::NOWN; ++i) { if (h->own[i]) cudaFree(h->own[i]); cudaEventDestroy(h->own_free[i]); cudaEventDestroy(h->own_ready[i]); }
+    for (int i = 0; i < dlra_engine::NOWN; ++i) {
+        if (h->own[i]) cudaFree(h->own[i]);
+        if (h->own_free[i]) cudaEventDestroy(h->own_free[i]);
+        if (h->own_ready[i]) cudaEventDestroy(h->own_ready[i]);
+    }
     h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release();
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (int i = 0; i < 8; ++i) if (h->user_events[i]) cudaEventDestroy(h->user_events[i]);
     de_release(h);
     h->gws2.release(); h->tws2.release(); h->wtmp2.release(); h->zcarry.k.release();
-    cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
-    cudaStreamDestroy(h->cx.stream); cudaStreamDestroy(h->copy_stream); cudaStreamDestroy(h->ax.stream);
+    if (h->cx.stream) cudaStreamDestroy(h->cx.stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->ax.stream) cudaStreamDestroy(h->ax.stream);
+    cudaGetLastError();   // a partially constructed handle may have produced sticky-free errors above
     delete h;
     return DLRA_OK;
 }

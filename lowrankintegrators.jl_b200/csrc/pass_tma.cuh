@@ -353,11 +353,9 @@ inline void launch_pass(dlra_engine* e, const Delta& d, int rc, const double* Vf
     using SM = PassSmem<RT, DO_K, DO_L, DIFF>;
     static_assert(SM::NST >= 2, "pipeline needs at least two stages");
     auto kern = pass_kernel<RT, DO_K, DO_L, DIFF>;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_this_device(attr_devs))
         DLRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-        attr = true;
-    }
     CUtensorMap mapA = make_map_2d(d.A, e->n, e->m, d.lda, 16, PT_TJ, true);
     CUtensorMap mapP = DIFF ? make_map_2d(d.Aprev, e->n, e->m, d.ldap, 16, PT_TJ, true) : mapA;
     CUtensorMap mapU = DO_L ? make_map_2d(Uf, e->n, rc, ldu, 16, RT, true) : mapA;

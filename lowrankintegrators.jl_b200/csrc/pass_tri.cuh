@@ -251,11 +251,9 @@ inline void tri_pass_launch(dlra_engine* e, const double* A2, int64_t ld2, const
                             int64_t ldk, double* Lpart, int64_t ldlp, int nsub, int npanels) {
     using SM = TriSmem<16>;
     auto kern = tri_pass_kernel<16>;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_this_device(attr_devs))
         DLRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
-        attr = true;
-    }
     CUtensorMap m2 = make_map_2d(A2, e->n, e->m, ld2, 16, PT_TJ, true);
     CUtensorMap m1 = make_map_2d(A1, e->n, e->m, ld1, 16, PT_TJ, true);
     CUtensorMap m0 = make_map_2d(A0, e->n, e->m, ld0, 16, PT_TJ, true);

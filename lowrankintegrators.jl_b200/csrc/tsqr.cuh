@@ -378,11 +378,10 @@ inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, in
         return;
     }
     const unsigned nb = (unsigned)cdiv(rows, TSQR_BR);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_devs = 0;
+    if (first_use_on_this_device(attr_devs)) {
         DLRA_CUDA(cudaFuncSetAttribute(tsqr_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<8>::BYTES));
         DLRA_CUDA(cudaFuncSetAttribute(tsqr_reg_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<16>::BYTES));
-        attr_set = true;
     }
     if (CP == 8) tsqr_reg_kernel<8><<<nb, TSQR_NW * 32, TsqrSmem<8>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr, add);
     else tsqr_reg_kernel<16><<<nb, TSQR_NW * 32, TsqrSmem<16>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr, add);
