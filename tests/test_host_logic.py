@@ -172,3 +172,18 @@ def test_two_factor_needs_the_greedy_integrator(fake):
         lri.init(lri.MatrixDataProblem(_snaps(3), u2), lri.UnconventionalAlgorithm(), 1)
     with pytest.raises(TypeError):
         lri.init(lri.MatrixHybridProblem(lambda t: np.zeros((6, 5)), lri.LinearRHS(A=1.0), _u0(), (0.0, 1.0)), lri.GreedyIntegrator(), 0.1)
+
+
+@pytest.mark.parametrize("tf,dt", [(1.0, 0.25), (1.0, 0.3), (0.5, 0.1), (1.0, 1e-2), (2.0, 0.7)])
+def test_driver_time_grid_matches_the_oracle_restatement(fake, tf, dt):
+    # primitives.jl:68-104: init_sol pre-sizes floor((tf-t0)/dt)+1 entries on a linspace, the loop runs while (tf-t)/T > 1e-8 and
+    # update_sol! push!es once the pre-sized vector is full (step sizes that do not divide the span overshoot tf by one step)
+    from oracle import dlra_oracle as O
+    y = lambda t: np.full((6, 5), t)
+    sol = lri.solve(lri.MatrixDataProblem(y, _u0(), (0.0, tf)), lri.ProjectorSplitting(lri.PrimalLieTrotter()), dt)
+    X0 = O.SVDLikeRepresentation(np.eye(6)[:, :2], np.eye(2), np.eye(5)[:, :2])
+    osol = O.solve(O.MatrixDataProblem(lambda t: np.zeros((6, 5)), X0, (0.0, tf)), O.ProjectorSplitting(O.PrimalLieTrotter()), dt)
+    assert len(sol.Y) == len(osol.Y) and np.allclose(sol.t, osol.t, rtol=0, atol=1e-14)
+    steps = [c for c in fake.log[0].calls if c[0] == "ksl"]
+    assert len(steps) == len(osol.Y) - 1
+    assert np.allclose([c[2] for c in steps], [dt * k for k in range(len(steps))], atol=1e-12)      # t passed to every step
