@@ -141,6 +141,11 @@ int dlra_data_push_host(dlra_handle h, const double* A, int64_t ld, int kind);
 int dlra_rhs_set(dlra_handle h, const dlra_operator* A, const dlra_operator* B, const double* G,
                  int64_t ldg, const double* H, int64_t ldh, int q, const dlra_operator* D1,
                  const dlra_operator* D2, double c_had);
+/* Adds one two-sided term A_k·X·B_kᵀ to the installed right-hand side: F(X) += A_k·X·B_kᵀ (A_k: n x n, B_k: m x m, dense,
+ * CSR or scale·I).  Covers generators of the chemical-master-equation type, examples/markov_chain.jl:64-66
+ * (Σ_r A_r .* (S_r·P·T_r) − Asum .* P: the rank-one Hadamard weights are diagonal scalings folded into the sparse
+ * operators).  dlra_rhs_set clears the list.  NOT VALIDATED ON HARDWARE in round 1 (tests gated by DLRA_UNVALIDATED=1). */
+int dlra_rhs_add_term(dlra_handle h, const dlra_operator* A, const dlra_operator* B);
 /* K_alg / S_alg / L_alg and their tolerances (Tsit5 defaults abstol=1e-6, reltol=1e-3) */
 int dlra_set_substepper(dlra_handle h, int flow, int ode, int nsub, double abstol, double reltol);
 

@@ -193,6 +193,10 @@ function normal_component(c::B200Cache, dY::Ptr{Float64}, ld::Integer; tol = 1e-
     return nrm[]
 end
 
+"F(X) += A*X*B' (two-sided term of the installed right-hand side; see dlra_rhs_add_term)"
+add_term!(c::B200Cache, A::Operator, B::Operator) =
+    check(c.h, ccall((:dlra_rhs_add_term, libdlra), Cint, (Handle, Ref{Operator}, Ref{Operator}), c.h, A, B))
+
 function init(prob, w::OnB200, dt)
     t0, tf = prob.tspan
     @assert tf > t0 "Integration in reverse time direction is not supported"

@@ -7,7 +7,7 @@ from .api import (DLRIntegrator, DLRSolution, DualLieTrotter, GreedyIntegrator, 
                   SVDLikeRepresentation, TwoFactorRepresentation, UnconventionalAlgorithm, init, solve, step,
                   truncate_to_tolerance, truncated_svd, truncated_svd_device, update_sol)
 from .engine import Engine, colmajor_device, empty_colmajor
-from .rhs import BurgersRHS, FactoredRHS, LinearRHS
+from .rhs import BurgersRHS, FactoredRHS, LinearRHS, SylvesterSumRHS
 from .distributed import attach_engine, comm_from_torch, row_shard
 
 step_ = step  # `step!`

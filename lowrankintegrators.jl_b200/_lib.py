@@ -51,6 +51,7 @@ SIGNATURES = {
     "dlra_data_push_host": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_int]),
     "dlra_rhs_set": (C.c_int, [handle_t, C.POINTER(Operator), C.POINTER(Operator), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                C.c_int, C.POINTER(Operator), C.POINTER(Operator), C.c_double]),
+    "dlra_rhs_add_term": (C.c_int, [handle_t, C.POINTER(Operator), C.POINTER(Operator)]),
     "dlra_set_substepper": (C.c_int, [handle_t, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]),
     "dlra_step_ksl": (C.c_int, [handle_t, C.c_int, C.c_double, C.c_double]),
     "dlra_step_bug": (C.c_int, [handle_t, C.c_double, C.c_double]),

@@ -174,8 +174,9 @@ __global__ void __launch_bounds__(128) hadamard_rows_kernel(int64_t rows, int p,
 // ------------------------------------------------------------------------------------------------------
 struct DeWork {
     DevBuf stages;      // 10 state-sized buffers for the RK schemes
-    DevBuf nbuf[3];     // n x W scratch: A·U / D1·X / D2·X
-    DevBuf mbuf[2];     // m x W scratch
+    DevBuf nbuf[4];     // n x W scratch: A·U / D1·X / D2·X / X·(VᵀB_kᵀV)
+    DevBuf mbuf[2];     // m x W scratch: B·V / X·(UᵀA_kᵀU)
+    DevBuf tsm;         // projected r x r matrices of the two-sided terms
     DevBuf tens[3];     // T_V, T_U, contraction scratch
     DevBuf tpart;       // partial tensors
     DevBuf small;       // r x r matrices
@@ -216,7 +217,7 @@ inline void de_release(dlra_engine* e) {
             for (auto& b : w->nbuf) b.release();
             for (auto& b : w->mbuf) b.release();
             for (auto& b : w->tens) b.release();
-            w->tpart.release(); w->small.release(); w->red.release();
+            w->tpart.release(); w->small.release(); w->red.release(); w->tsm.release();
             if (w->scal_host) cudaFreeHost(w->scal_host);
             delete w;
             reg.erase(reg.begin() + i);
@@ -247,6 +248,21 @@ inline void de_rhs_set(dlra_engine* e, const dlra_operator* A, const dlra_operat
     if (c_had != 0.0) DLRA_REQUIRE(r.D1.kind != DLRA_OP_NONE && r.D2.kind != DLRA_OP_NONE, "Hadamard term needs D1 and D2");
     e->rhs = r;
     de_work(e);
+}
+
+// one more term A_k·X·B_kᵀ of the right-hand side (operators as in de_rhs_set; identity-scaled allowed on either side)
+inline void de_rhs_add_term(dlra_engine* e, const dlra_operator* A, const dlra_operator* B) {
+    DLRA_REQUIRE(e->rhs.set, "install the right-hand side first (dlra_rhs_set; all of its terms may be empty)");
+    DLRA_REQUIRE(A && B, "both operators of a two-sided term are needed (use DLRA_OP_IDENTITY_SCALED for the identity)");
+    auto chk = [&](const dlra_operator* op, int64_t dim) {
+        DLRA_REQUIRE(op->kind == DLRA_OP_DENSE || op->kind == DLRA_OP_CSR || op->kind == DLRA_OP_IDENTITY_SCALED, "unknown operator kind");
+        if (op->kind != DLRA_OP_IDENTITY_SCALED) DLRA_REQUIRE(op->rows == dim && op->cols == dim, "operator of a two-sided term has the wrong shape");
+        if (op->kind == DLRA_OP_DENSE) DLRA_REQUIRE(op->dense && op->ld >= dim, "dense operator pointer / ld");
+        if (op->kind == DLRA_OP_CSR) DLRA_REQUIRE(op->rowptr && op->colind && op->values, "CSR operator pointers");
+    };
+    chk(A, e->n); chk(B, e->m);
+    DLRA_REQUIRE(e->rhs.terms.size() < 64, "at most 64 two-sided terms");
+    e->rhs.terms.emplace_back(*A, *B);
 }
 
 // T (p^3) = Σ_rows P .* Q .* W triple products, deterministic two-stage reduction
@@ -441,6 +457,9 @@ struct SideFlow : FlowRhs {
     double c_had; const double* T; // r^3 tensor or null
     const dlra_operator* d1; const dlra_operator* d2;           // K-flow: applied to X; L-flow: null (operands are X itself)
     double* s1; double* s2;        // rows x r scratch for D1·X, D2·X
+    // two-sided terms Σ_k Op_k·X·Tsm_k: Op_k = A_k (K-flow) or B_k (L-flow), Tsm_k = VᵀB_kᵀV or UᵀA_kᵀU (r x r, ld r, packed)
+    const std::vector<std::pair<dlra_operator, dlra_operator>>* terms = nullptr;
+    bool side_is_n = true; const double* Tsm = nullptr; double* s3 = nullptr;
     void eval(const double* X, double* out, double) override {
         Ctx& cx = e->cx;
         if (op && op->kind != DLRA_OP_NONE) apply_op(cx, *op, rows, r, X, rows, out, rows, 1.0, 0.0);
@@ -456,6 +475,12 @@ struct SideFlow : FlowRhs {
             cx.launches++;
             DLRA_CUDA(cudaGetLastError());
         }
+        if (terms)
+            for (size_t k = 0; k < terms->size(); ++k) {
+                const dlra_operator& opk = side_is_n ? (*terms)[k].first : (*terms)[k].second;
+                gemm_nn(cx, rows, r, r, X, rows, nullptr, 0, Tsm + (int64_t)k * r * r, r, false, s3, rows, 1.0, 0.0);   // X·Tsm_k
+                apply_op(cx, opk, rows, r, s3, rows, out, rows, 1.0, 1.0);                                             // += Op_k·(X·Tsm_k)
+            }
     }
 };
 
@@ -496,6 +521,15 @@ inline void de_K_flow(dlra_engine* e, double* K, int r, const double* V, double 
         if (R.D2.kind == DLRA_OP_IDENTITY_SCALED) f.c_had *= R.D2.scale;
     }
     f.s1 = w->nbuf[1].p; f.s2 = w->nbuf[2].p;
+    if (!R.terms.empty()) {   // Tsm_k = VᵀB_kᵀV = (B_k·V)ᵀ·V
+        w->tsm.ensure((int64_t)R.terms.size() * r * r, cx.stream);
+        w->nbuf[3].ensure(n * (int64_t)r, cx.stream);
+        for (size_t k = 0; k < R.terms.size(); ++k) {
+            apply_op(cx, R.terms[k].second, m, r, V, m, w->mbuf[0].p, m, 1.0, 0.0);
+            gemm_tn(cx, m, r, r, w->mbuf[0].p, m, nullptr, 0, V, m, w->tsm.p + (int64_t)k * r * r, r, 1.0, 0.0, e->gws.p);
+        }
+        f.terms = &R.terms; f.side_is_n = true; f.Tsm = w->tsm.p; f.s3 = w->nbuf[3].p;
+    }
     // K lives in an engine buffer with ld == n (dense): integrate in place
     ode_advance(e, e->sub[DLRA_FLOW_K], f, n * (int64_t)r, K, t, dt);
 }
@@ -533,6 +567,15 @@ inline void de_L_flow(dlra_engine* e, double* L, int r, const double* U, double 
     SideFlow f;
     f.e = e; f.w = w; f.rows = m; f.r = r; f.op = &R.B; f.Msm = Au; f.Fc = R.H; f.ldf = R.ldh; f.q = R.q; f.Fsm = Gu;
     f.c_had = chad; f.T = T; f.d1 = nullptr; f.d2 = nullptr; f.s1 = nullptr; f.s2 = nullptr;
+    if (!R.terms.empty()) {   // Tsm_k = UᵀA_kᵀU = (A_k·U)ᵀ·U
+        w->tsm.ensure((int64_t)R.terms.size() * r * r, cx.stream);
+        w->mbuf[1].ensure(m * (int64_t)r, cx.stream);
+        for (size_t k = 0; k < R.terms.size(); ++k) {
+            apply_op(cx, R.terms[k].first, n, r, U, n, w->nbuf[0].p, n, 1.0, 0.0);
+            gemm_tn(cx, n, r, r, w->nbuf[0].p, n, nullptr, 0, U, n, w->tsm.p + (int64_t)k * r * r, r, 1.0, 0.0, e->gws.p);
+        }
+        f.terms = &R.terms; f.side_is_n = false; f.Tsm = w->tsm.p; f.s3 = w->mbuf[1].p;
+    }
     ode_advance(e, e->sub[DLRA_FLOW_L], f, m * (int64_t)r, L, t, dt, carry);
 }
 
@@ -541,6 +584,8 @@ struct CoreFlow : FlowRhs {
     dlra_engine* e; int p, q; double sign;
     const double* Auu; const double* Bvv; const double* GH; bool has_gh;
     double c_had; const double* TU; const double* TV; double* Y1; double* Y2;
+    // two-sided terms: Σ_k (UᵀA_kU)·S·(VᵀB_kᵀV); Tuu: nterms x (p x p, ld p), Tvv: nterms x (q x q, ld q), Ttmp: p x q
+    int nterms = 0; const double* Tuu = nullptr; const double* Tvv = nullptr; double* Ttmp = nullptr;
     void eval(const double* S, double* out, double) override {
         Ctx& cx = e->cx;
         small_gemm(cx, p, q, p, Auu, p, false, S, p, false, out, p, sign, 0.0);
@@ -554,6 +599,10 @@ struct CoreFlow : FlowRhs {
                 small_gemm(cx, p, p, q, Y1 + (int64_t)d * p * q, p, false, S, p, true, Y2 + (int64_t)d * p * p, p, 1.0, 0.0);
             // out[c,d] += sign·c_had · Σ_{a',b'} TU[(a',b'), c] · Y2[(a',b'), d]     (TUᵀ·Y2 with p^2 rows)
             small_gemm(cx, p, q, p * p, TU, p * p, true, Y2, p * p, false, out, p, sign * c_had, 1.0);
+        }
+        for (int k = 0; k < nterms; ++k) {
+            small_gemm(cx, p, q, p, Tuu + (int64_t)k * p * p, p, false, S, p, false, Ttmp, p, 1.0, 0.0);
+            small_gemm(cx, p, q, q, Ttmp, p, false, Tvv + (int64_t)k * q * q, q, false, out, p, sign, 1.0);
         }
     }
 };
@@ -604,6 +653,18 @@ inline void de_S_flow(dlra_engine* e, double* S, int p, int q, const double* U, 
         tensor3(e, w, m, q, V, m, V, m, V, m, w->tens[0].p);
         w->tens[2].ensure((int64_t)p * q * q + (int64_t)p * p * q, cx.stream);
         f.TU = w->tens[1].p; f.TV = w->tens[0].p; f.Y1 = w->tens[2].p; f.Y2 = w->tens[2].p + (int64_t)p * q * q;
+    }
+    if (!R.terms.empty()) {
+        const int64_t nt = (int64_t)R.terms.size();
+        w->tsm.ensure(nt * ((int64_t)p * p + (int64_t)q * q) + (int64_t)p * q, cx.stream);
+        double* Tuu = w->tsm.p; double* Tvv = Tuu + nt * p * p; double* Ttmp = Tvv + nt * q * q;
+        for (int64_t k = 0; k < nt; ++k) {
+            apply_op(cx, R.terms[k].first, n, p, U, n, w->nbuf[0].p, n, 1.0, 0.0);
+            gemm_tn(cx, n, p, p, U, n, nullptr, 0, w->nbuf[0].p, n, Tuu + k * p * p, p, 1.0, 0.0, e->gws.p);          // Uᵀ(A_k U)
+            apply_op(cx, R.terms[k].second, m, q, V, m, w->mbuf[0].p, m, 1.0, 0.0);
+            gemm_tn(cx, m, q, q, w->mbuf[0].p, m, nullptr, 0, V, m, Tvv + k * q * q, q, 1.0, 0.0, e->gws.p);          // (B_k V)ᵀV
+        }
+        f.nterms = (int)nt; f.Tuu = Tuu; f.Tvv = Tvv; f.Ttmp = Ttmp;
     }
     copy_mat(cx, p, q, S, W, false, Sd, p);
     ode_advance(e, e->sub[DLRA_FLOW_S], f, (int64_t)p * q, Sd, t, dt);

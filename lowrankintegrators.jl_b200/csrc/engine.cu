@@ -830,6 +830,13 @@ extern "C" int dlra_rhs_set(dlra_handle h, const dlra_operator* A, const dlra_op
     DLRA_API_END(h)
 }
 
+extern "C" int dlra_rhs_add_term(dlra_handle h, const dlra_operator* A, const dlra_operator* B) {
+    DLRA_API_BEGIN(h)
+    de_rhs_add_term(h, A, B);
+    h->zcarry.valid = false;
+    DLRA_API_END(h)
+}
+
 extern "C" int dlra_set_substepper(dlra_handle h, int flow, int ode, int nsub, double abstol, double reltol) {
     DLRA_API_BEGIN(h)
     DLRA_REQUIRE(flow >= 0 && flow <= 2, "flow must be DLRA_FLOW_K|S|L");

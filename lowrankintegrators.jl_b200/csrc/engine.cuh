@@ -57,6 +57,8 @@ struct RhsCfg {
     const double* H = nullptr; int64_t ldh = 0;
     int q = 0;
     double c_had = 0.0;
+    // two-sided terms  Σ_k A_k·X·B_kᵀ  (dlra_rhs_add_term)
+    std::vector<std::pair<dlra_operator, dlra_operator>> terms;
 };
 
 }  // namespace dlra

@@ -181,29 +181,31 @@ class Engine:
     def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0):
         self._ck(self.lib.dlra_set_substepper(self.h, flow, ode, nsub, abstol, reltol))
 
+    @staticmethod
+    def _operator(x, keep):
+        """dlra_operator for a Python scalar (s*I), a CSR tuple (rowptr int64, colind int32, values fp64, shape) of CUDA tensors,
+        or a dense CUDA matrix; tensors that must stay alive are appended to `keep`."""
+        if x is None:
+            return None
+        o = L.Operator()
+        if np.isscalar(x):
+            o.kind, o.scale = L.OP_IDENTITY_SCALED, float(x)
+            return o
+        if isinstance(x, tuple):
+            rowptr, colind, values, shape = x
+            keep.extend([rowptr, colind, values])
+            o.kind, o.rows, o.cols = L.OP_CSR, shape[0], shape[1]
+            o.rowptr, o.colind, o.values, o.scale = rowptr.data_ptr(), colind.data_ptr(), values.data_ptr(), 1.0
+            return o
+        x = colmajor_device(x)
+        keep.append(x)
+        o.kind, o.rows, o.cols, o.dense, o.scale = L.OP_DENSE, x.shape[0], x.shape[1], x.data_ptr(), 1.0
+        o.ld = x.stride(1) if x.shape[1] > 1 else x.shape[0]
+        return o
+
     def rhs_set(self, A=None, B=None, G=None, H=None, D1=None, D2=None, c_had=0.0):
         keep = []
-
-        def op(x):
-            if x is None:
-                return None
-            o = L.Operator()
-            if np.isscalar(x):
-                o.kind, o.scale = L.OP_IDENTITY_SCALED, float(x)
-                return o
-            if isinstance(x, tuple):  # CSR: (rowptr int64, colind int32, values fp64, shape) as CUDA tensors
-                rowptr, colind, values, shape = x
-                keep.extend([rowptr, colind, values])
-                o.kind, o.rows, o.cols = L.OP_CSR, shape[0], shape[1]
-                o.rowptr, o.colind, o.values, o.scale = rowptr.data_ptr(), colind.data_ptr(), values.data_ptr(), 1.0
-                return o
-            x = colmajor_device(x)
-            keep.append(x)
-            o.kind, o.rows, o.cols, o.dense, o.scale = L.OP_DENSE, x.shape[0], x.shape[1], x.data_ptr(), 1.0
-            o.ld = x.stride(1) if x.shape[1] > 1 else x.shape[0]
-            return o
-
-        ops = [op(A), op(B), op(D1), op(D2)]
+        ops = [self._operator(x, keep) for x in (A, B, D1, D2)]
         refs = [C.byref(o) if o is not None else None for o in ops]
         q = 0
         pg = ph = None
@@ -217,6 +219,16 @@ class Engine:
         self._after_torch()  # after every layout conversion above has been queued on torch's stream
         self._ck(self.lib.dlra_rhs_set(self.h, refs[0], refs[1], pg, ldg, ph, ldh, q, refs[2], refs[3], float(c_had)))
         self._keep["rhs"] = (keep, ops)
+        self._keep["rhs_terms"] = []
+
+    def rhs_add_term(self, A, B):
+        """F(X) += A*X*B' (two-sided term; A, B as accepted by rhs_set, a scalar s meaning s*I)."""
+        keep = []
+        oa, ob = self._operator(A, keep), self._operator(B, keep)
+        assert oa is not None and ob is not None, "a two-sided term needs both operators (use 1.0 for the identity)"
+        self._after_torch()
+        self._ck(self.lib.dlra_rhs_add_term(self.h, C.byref(oa), C.byref(ob)))
+        self._keep.setdefault("rhs_terms", []).append((keep, oa, ob))
 
     # -- steps -------------------------------------------------------------------------------------
     def step_ksl(self, order, t=0.0, dt=1.0):

@@ -1,5 +1,6 @@
 """Seeded synthetic inputs shared by the oracle tests and the GPU parity tests."""
 import numpy as np
+import scipy.sparse as sp
 from scipy.linalg import expm
 
 
@@ -63,3 +64,22 @@ def burgers_truth(n, xi_grid, t_grid, nu=0.005, length=np.pi, substeps=20):
             rho = rho + (h / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
         out.append(rho.copy())
     return out, F
+
+
+def cme_operators(N, k1=30.0, k2=1.0, k3=10.0, k4=1.0, theta=1.0):
+    """examples/markov_chain.jl:10-66: propensity factors ax, ay and shift operators of the two-species network."""
+    x = np.arange(N, dtype=np.float64)
+    ax = [np.ones(N), k2 * x, k3 / (1 + x), np.ones(N)]
+    ay = [k1 / (1 + (x / theta) ** 3), np.ones(N), np.ones(N), k4 * x]
+    nu = [(1, 0), (-1, 0), (0, 1), (0, -1)]
+
+    def shift(s):
+        return sp.eye(N, k=-s, format="csr") if s != 0 else sp.identity(N, format="csr")
+    terms = []
+    for r in range(4):
+        Sr, Sc = shift(nu[r][0]), shift(nu[r][1])              # Srows[r], Scols[r]' = shift(nu_y)'
+        a_sh, b_sh = Sr @ ax[r], Sc @ ay[r]                      # A[r] = Srows*TwoFactor(ax,ay)*Scols: shifted rank-one weights
+        # A[r] .* (Srows P Scols) = diag(a_sh)·Srows·P·Scols·diag(b_sh)
+        terms.append((sp.csr_matrix(sp.diags(a_sh) @ Sr), sp.csr_matrix(sp.diags(b_sh) @ Sc)))   # (A_k, B_k) with B_kᵀ = Scols·diag
+        terms.append((sp.csr_matrix(-sp.diags(ax[r])), sp.csr_matrix(sp.diags(ay[r]))))           # − Asum .* P
+    return terms

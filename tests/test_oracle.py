@@ -232,3 +232,25 @@ def test_adaptive_tsit5_meets_tolerance_and_reaches_the_end_exactly():
         assert prev is None or st.naccept > prev                  # tighter tolerance -> more steps
         assert st.nreject <= st.naccept
         prev = st.naccept
+
+
+def test_reference_markov_chain_example_reduced():
+    # examples/markov_chain.jl at reduced size (N=64 instead of 600, Tf=0.4): BUG on the chemical master equation, written as the
+    # sum of two-sided terms Σ_k A_k·P·B_kᵀ the engine evaluates (dlra_rhs_add_term), tracks the directly integrated solution
+    from tests.problems import cme_operators
+    N = 64
+    terms = [(A.toarray(), B.toarray()) for A, B in cme_operators(N)]
+    f = lambda P, t: sum(A @ P @ B.T for A, B in terms)
+    xs = np.arange(1, N + 1)
+    D = np.array([[0.03, 0.01], [0.01, 0.02]])
+    P0 = np.array([[np.exp(-np.array([x - 20, y - 20]) @ D @ np.array([x - 20, y - 20])) for y in xs] for x in xs])
+    P0 /= P0.sum()
+    X0 = O.truncated_svd(P0, tol=1e-6)                                          # markov_chain.jl:86
+    dt, Tf = 2e-2, 0.4
+    sol = O.solve(O.MatrixDEProblem(f, X0, (0.0, Tf)), O.UnconventionalAlgorithm(), dt)
+    P, h = P0.copy(), dt / 20
+    for _ in range(int(round(Tf / h))):
+        k1 = f(P, 0); k2 = f(P + 0.5 * h * k1, 0); k3 = f(P + 0.5 * h * k2, 0); k4 = f(P + h * k3, 0)
+        P = P + (h / 6) * (k1 + 2 * k2 + 2 * k3 + k4)
+    assert abs(P.sum() - 1) < 1e-9                                              # probability is conserved (mass only leaves at the truncation boundary)
+    assert rel_fro(sol.Y[-1].full(), P) < 1e-3
