@@ -39,7 +39,10 @@ enum {
 /* dlra_create flags */
 enum {
     DLRA_RANK_ADAPTIVE = 1,  /* size workspaces for the augmented 2r bases of the rank-adaptive integrator */
-    DLRA_FORCE_GENERIC = 2   /* debugging: use the generic (non-TMA, non-DMMA) contraction kernels only */
+    DLRA_FORCE_GENERIC = 2,  /* debugging: use the generic (non-TMA, non-DMMA) contraction kernels only */
+    DLRA_AUG_BASIS_FIRST = 4 /* rank-adaptive step: factor the augmented bases as [U0 | K], [V0 | L] instead of [K | U0], [L | V0]
+                              * (same span, hence the same U·S·Vᵀ and ranks; the leading panel is already orthonormal and needs no
+                              * TSQR).  Opt-in: not validated on hardware in round 1. */
 };
 
 /* KSL orders: PrimalLieTrotter / DualLieTrotter / Strang (projector_splitting.jl:1-3) */

@@ -12,7 +12,7 @@ c_i64_p = C.POINTER(C.c_int64)
 handle_t = C.c_void_p
 
 OK, EINVAL, ECUDA, ENCCL, ESTATE, ENOMEM, EUNSUPPORTED = range(7)
-RANK_ADAPTIVE, FORCE_GENERIC = 1, 2
+RANK_ADAPTIVE, FORCE_GENERIC, AUG_BASIS_FIRST = 1, 2, 4
 KSL_PRIMAL, KSL_DUAL, KSL_STRANG = 0, 1, 2
 DATA_SNAPSHOT, DATA_DELTA = 0, 1
 FLOW_K, FLOW_S, FLOW_L = 0, 1, 2

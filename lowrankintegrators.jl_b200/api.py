@@ -268,7 +268,8 @@ def _has_snapshot(y, tspan, t, ahead):
     return isinstance(t, (int, np.integer)) and (t + ahead - 1) < len(y) and (t + ahead) <= tspan[1]
 
 
-def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False, lookahead=True, resume=None) -> DLRIntegrator:
+def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False, lookahead=True, resume=None,
+         aug_basis_first=False) -> DLRIntegrator:
     """init(prob, alg, dt): projector_splitting.jl:107-115, unconventional.jl:109-119,
     rank_adaptive_unconventional.jl:94-104, greedy_integrator.jl:49-59.  `comm` = "torch" (use the initialised torch.distributed group to distribute
     a fresh ncclUniqueId) or (nranks, rank, unique_id) row-shards the problem: every rank passes ITS row block of u0.U
@@ -292,7 +293,8 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     if adaptive:
         rmax = int(min(alg.rmax, 128, m // 2 if m >= 2 else 1))
         rmax = max(rmax, r0)
-    eng = Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic)
+    eng = (Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic, aug_basis_first=True)
+           if aug_basis_first else Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic))
     if comm == "torch":  # torch.distributed only hands out the IPC handles / the ncclUniqueId
         from .distributed import attach_engine
         attach_engine(eng)

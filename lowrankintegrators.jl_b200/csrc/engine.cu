@@ -369,10 +369,10 @@ static void ensure_qr_ws(Side sd, int64_t rows, int C) {
     }
 }
 // thin QR of an n-side (row sharded) matrix, in place
-static void qr_nside(dlra_handle h, double* A, int C, double* R) {
+static void qr_nside(dlra_handle h, double* A, int C, double* R, int ortho_cols = 0) {
     Side sd = main_side(h);
     ensure_qr_ws(sd, h->n, C);
-    thin_qr(h->cx, h->comm, h->n, C, A, h->n, A, h->n, R, h->W, h->tws.p, h->gws.p, h->wtmp.p);
+    thin_qr(h->cx, h->comm, h->n, C, A, h->n, A, h->n, R, h->W, h->tws.p, h->gws.p, h->wtmp.p, ortho_cols);
 }
 // thin QR of (A + Ua*Sa) in place; the rank-r update rides on the panel load of the first TSQR level when it can
 static void qr_nside_plus(dlra_handle h, double* A, int C, const double* Ua, const double* Sa, int k) {
@@ -387,9 +387,9 @@ static void qr_nside_plus(dlra_handle h, double* A, int C, const double* Ua, con
     }
 }
 // thin QR of an m-side (replicated) matrix, in place, computed redundantly on every rank
-static void qr_mside(dlra_handle h, Side sd, double* A, int C, double* R) {
+static void qr_mside(dlra_handle h, Side sd, double* A, int C, double* R, int ortho_cols = 0) {
     ensure_qr_ws(sd, h->m, C);
-    thin_qr(*sd.cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, sd.tws->p, sd.gws->p, sd.wtmp->p);
+    thin_qr(*sd.cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, sd.tws->p, sd.gws->p, sd.wtmp->p, ortho_cols);
 }
 // C (p x q, ld W) = A' * B over the sharded n dimension (+ all-reduce)
 static void gram_nside(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
@@ -587,20 +587,26 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     int rcap = (int)std::min<int64_t>(rcap64, (int64_t)h->rmax);
     rcap = std::min(rcap, r2);
     double *Kh = h->UB, *Lh = h->VB;   // [K U0] -> Uhat ; [L V0] -> Vhat
-    gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, Kh, n, 1.0, 0.0);
+    // DLRA_AUG_BASIS_FIRST: [U0 K], [V0 L] — same span; the leading (orthonormal) panel then skips its factorisation
+    const bool first = (h->flags & DLRA_AUG_BASIS_FIRST) != 0;
+    double* Kc = first ? Kh + (int64_t)r * n : Kh;          // where K / L are formed
+    double* Lc = first ? Lh + (int64_t)r * m : Lh;
+    double* Uc = first ? Kh : Kh + (int64_t)r * n;          // where the copies of U0 / V0 go
+    double* Vc = first ? Lh : Lh + (int64_t)r * m;
+    gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, Kc, n, 1.0, 0.0);
     if (sc.is_data) {
-        pass_KL(h, sc.d, r, h->V, m, h->U, n, Kh, n, Lh, m, h->V, m, h->S, W);
+        pass_KL(h, sc.d, r, h->V, m, h->U, n, Kc, n, Lc, m, h->V, m, h->S, W);
     } else {
-        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, Lh, m, 1.0, 0.0);
-        de_K_flow(h, Kh, r, h->V, sc.t, sc.dt);
-        de_L_flow(h, Lh, r, h->U, sc.t, sc.dt);
+        gemm_nn(cx, m, r, r, h->V, m, nullptr, 0, h->S, W, true, Lc, m, 1.0, 0.0);
+        de_K_flow(h, Kc, r, h->V, sc.t, sc.dt);
+        de_L_flow(h, Lc, r, h->U, sc.t, sc.dt);
     }
-    copy_mat(cx, n, r, h->U, n, false, Kh + (int64_t)r * n, n);          // Uhat[:, r+1:end] = U0
-    copy_mat(cx, m, r, h->V, m, false, Lh + (int64_t)r * m, m);
+    copy_mat(cx, n, r, h->U, n, false, Uc, n);             // Uhat[:, r+1:end] = U0 (reference order) | Uhat[:, 1:r] = U0
+    copy_mat(cx, m, r, h->V, m, false, Vc, m);
     fork_aux(h);
-    qr_mside(h, aux_side(h), Lh, r2, nullptr);
+    qr_mside(h, aux_side(h), Lh, r2, nullptr, first ? r : 0);
     gram_mside(h, aux_side(h), r2, r, Lh, h->V, h->N);                   // N = Vhat'*V0
-    qr_nside(h, Kh, r2, nullptr);
+    qr_nside(h, Kh, r2, nullptr, first ? r : 0);
     gram_nside_local(h, r2, r, Kh, h->U, h->M);                          // M = Uhat'*U0 (2r x r), local rows
     join_aux(h);
     if (sc.is_data) {

@@ -444,8 +444,9 @@ inline void tsqr(Ctx& cx, Comm& comm, int64_t rows, int C, const double* A, int6
 // A is overwritten; Q may alias A.  R (C x C, ldr) optional.  gws: gemm_tn scratch, Wtmp: thin_qr_wtmp(C) doubles, tws: tsqr scratch.
 inline int64_t thin_qr_wtmp(int C) { return (int64_t)2 * C * TSQR_MAXC + 4 * TSQR_MAXC * TSQR_MAXC; }
 
+// ortho_cols: number of leading columns of A that are already orthonormal (panels entirely inside them are taken as they are).
 inline void thin_qr(Ctx& cx, Comm& comm, int64_t rows, int C, double* A, int64_t lda, double* Q, int64_t ldq, double* R, int64_t ldr,
-                    double* tws, double* gws, double* Wtmp) {
+                    double* tws, double* gws, double* Wtmp, int ortho_cols = 0) {
     if (C <= TSQR_MAXC) {
         tsqr(cx, comm, rows, C, A, lda, Q, ldq, R, ldr, tws);
         return;
@@ -460,6 +461,11 @@ inline void thin_qr(Ctx& cx, Comm& comm, int64_t rows, int C, double* A, int64_t
         const int cb = std::min(TSQR_MAXC, C - c0);
         double* Ap = A + (int64_t)c0 * lda;
         double* Qp = Q + (int64_t)c0 * ldq;
+        if (c0 + cb <= ortho_cols) {   // already orthonormal (and orthogonal to the earlier panels, which lie in the same block)
+            if (Qp != Ap) copy_mat(cx, rows, cb, Ap, lda, false, Qp, ldq);
+            if (R) fill_mat(cx, cb, cb, R + c0 + (int64_t)c0 * ldr, ldr, 0.0, 1.0);
+            continue;
+        }
         if (c0 == 0) {
             tsqr(cx, comm, rows, cb, Ap, lda, Qp, ldq, R, ldr, tws);
             continue;

@@ -48,7 +48,7 @@ def _ptr_ld(x):
 
 
 class Engine:
-    def __init__(self, n_local, m, r0, rmax=None, rank_adaptive=False, device=None, force_generic=False):
+    def __init__(self, n_local, m, r0, rmax=None, rank_adaptive=False, device=None, force_generic=False, aug_basis_first=False):
         self.lib = L.load()
         if torch is not None and torch.cuda.is_available():
             device = torch.cuda.current_device() if device is None else device
@@ -57,7 +57,8 @@ class Engine:
         self.device = int(device)
         self.n, self.m = int(n_local), int(m)
         rmax = r0 if rmax is None else rmax
-        flags = (L.RANK_ADAPTIVE if rank_adaptive else 0) | (L.FORCE_GENERIC if force_generic else 0)
+        flags = ((L.RANK_ADAPTIVE if rank_adaptive else 0) | (L.FORCE_GENERIC if force_generic else 0)
+                 | (L.AUG_BASIS_FIRST if aug_basis_first else 0))
         h = L.handle_t()
         rc = self.lib.dlra_create(self.device, self.n, self.m, int(r0), int(rmax), flags, C.byref(h))
         if rc != L.OK:
