@@ -23,7 +23,8 @@ def main():
         for kind, kname in ((L.DATA_DELTA, "delta"), (L.DATA_SNAPSHOT, "snapshot")):
             if alg in ("greedy", "greedy2", "normal") and kind == L.DATA_DELTA: continue
             if kname not in kinds: continue
-            eng = lri.Engine(n, m, r, rmax=r, rank_adaptive=(alg == "rabug"))
+            eng = lri.Engine(n, m, r, rmax=r, rank_adaptive=(alg == "rabug"),
+                             aug_basis_first=(alg == "rabug" and os.environ.get("DLRA_AUG") == "1"))
             eng.set_factors(U0, S0, V0)
             eng.data_init(snaps[0])
             look = len(sys.argv) > 7 and sys.argv[7] == "lookahead" and alg == "bug" and kind == L.DATA_SNAPSHOT
