@@ -1,5 +1,6 @@
 // Shared helpers for libdlra.so (sm_100a only).
 #pragma once
+#include <nvtx3/nvToolsExt.h>
 #include <cuda_runtime.h>
 #include <cuda.h>
 #include <cstdint>
@@ -30,6 +31,14 @@ struct CudaError : std::runtime_error {
     do {                                                                                           \
         if (!(cond)) throw ::dlra::CudaError(1, std::string(msg) + " [" #cond "]");                \
     } while (0)
+
+// NVTX range for the profilers' timelines (header-only NVTX v3: a no-op unless a tool injects itself)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // cudaFuncSetAttribute is per device: a host process that drives several GPUs (one handle each) must repeat it on each one.
 // `mask` is a function-local static; returns true the first time the calling kernel wrapper runs on the current device.

@@ -331,6 +331,7 @@ inline void tsit5_stages(dlra_engine* e, FlowRhs& f, int64_t N, const double* u,
 
 inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N, double* X, double t0, double dt,
                         FsalCarry* carry = nullptr) {
+    NvtxRange nvtx_ode("dlra:ode_advance");
     DeWork* w = de_work(e);
     Ctx& cx = e->cx;
     w->stages.ensure(10 * N, cx.stream);

@@ -370,12 +370,14 @@ static void ensure_qr_ws(Side sd, int64_t rows, int C) {
 }
 // thin QR of an n-side (row sharded) matrix, in place
 static void qr_nside(dlra_handle h, double* A, int C, double* R, int ortho_cols = 0) {
+    NvtxRange nvtx_qr("dlra:qr_nside");
     Side sd = main_side(h);
     ensure_qr_ws(sd, h->n, C);
     thin_qr(h->cx, h->comm, h->n, C, A, h->n, A, h->n, R, h->W, h->tws.p, h->gws.p, h->wtmp.p, ortho_cols);
 }
 // thin QR of (A + Ua*Sa) in place; the rank-r update rides on the panel load of the first TSQR level when it can
 static void qr_nside_plus(dlra_handle h, double* A, int C, const double* Ua, const double* Sa, int k) {
+    NvtxRange nvtx_qr("dlra:qr_nside_plus");
     if (C <= TSQR_MAXC && h->n > 128) {
         Side sd = main_side(h);
         ensure_qr_ws(sd, h->n, C);
@@ -388,6 +390,7 @@ static void qr_nside_plus(dlra_handle h, double* A, int C, const double* Ua, con
 }
 // thin QR of an m-side (replicated) matrix, in place, computed redundantly on every rank
 static void qr_mside(dlra_handle h, Side sd, double* A, int C, double* R, int ortho_cols = 0) {
+    NvtxRange nvtx_qr("dlra:qr_mside");
     ensure_qr_ws(sd, h->m, C);
     thin_qr(*sd.cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, sd.tws->p, sd.gws->p, sd.wtmp->p, ortho_cols);
 }
@@ -442,6 +445,7 @@ struct StepCtx {
 // unconventional (BUG) step — unconventional.jl:133-157, SURVEY.md A.2
 // ---------------------------------------------------------------------------------------------------
 static void bug_step(dlra_handle h, const StepCtx& sc) {
+    NvtxRange nvtx_step("dlra:bug_step");
     Ctx& cx = h->cx;
     const int r = h->r;
     const int64_t n = h->n, m = h->m, W = h->W;
@@ -512,6 +516,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
 // projector splitting (KSL) — projector_splitting.jl:129-152 (primal), 166-189 (dual), SURVEY.md A.1
 // ---------------------------------------------------------------------------------------------------
 static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
+    NvtxRange nvtx_step("dlra:ksl_primal_step");
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;
@@ -541,6 +546,7 @@ static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
 }
 
 static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
+    NvtxRange nvtx_step("dlra:ksl_dual_step");
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;
@@ -576,6 +582,7 @@ static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
 // rank-adaptive BUG — rank_adaptive_unconventional.jl:194-233 + alg_recache :133-169, SURVEY.md A.3
 // ---------------------------------------------------------------------------------------------------
 static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rcap64, int* r_new_out, int* changed) {
+    NvtxRange nvtx_step("dlra:rabug_step");
     Ctx& cx = h->cx;
     const int r = h->r;
     const int r2 = 2 * r;
@@ -640,6 +647,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
 // greedy re-projection — greedy_integrator.jl:94-104
 // ---------------------------------------------------------------------------------------------------
 static void greedy_step(dlra_handle h, const Delta& x) {
+    NvtxRange nvtx_step("dlra:greedy_step");
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;
@@ -663,6 +671,7 @@ static void greedy_step(dlra_handle h, const Delta& x) {
 // Z lives in the V slot, S stays at identity.
 // ---------------------------------------------------------------------------------------------------
 static void greedy_two_factor_step(dlra_handle h, const Delta& x, int mode, bool carry_fsal, double t, double dt) {
+    NvtxRange nvtx_step("dlra:greedy_two_factor_step");
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;

@@ -249,6 +249,7 @@ tri_pass_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant_
 inline void tri_pass_launch(dlra_engine* e, const double* A2, int64_t ld2, const double* A1, int64_t ld1, const double* A0, int64_t ld0,
                             int rc, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu, double* W, int64_t ldw, double* K,
                             int64_t ldk, double* Lpart, int64_t ldlp, int nsub, int npanels) {
+    NvtxRange nvtx_pass("dlra:tri_pass");
     using SM = TriSmem<16>;
     auto kern = tri_pass_kernel<16>;
     static unsigned long long attr_devs = 0;

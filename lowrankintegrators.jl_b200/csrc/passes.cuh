@@ -20,6 +20,7 @@ inline void pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int
                     double* K, int64_t ldk, double* Lout, int64_t ldl, const double* Vi = nullptr, int64_t ldvi = 0,
                     const double* Si = nullptr, int64_t ldsi = 0) {
     Ctx& cx = e->cx;
+    NvtxRange nvtx_pass("dlra:pass_KL");
     if (!(e->flags & DLRA_FORCE_GENERIC) && tma_pass_supported(e->n, e->m, d)) {
         tma_pass_KL(e, d, r, Vf, ldv, Uf, ldu, K, ldk, Lout, ldl, Vi, ldvi, Si, ldsi);   // timed per kernel launch inside
         return;
@@ -44,6 +45,7 @@ inline void pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int
 inline void pass_S(dlra_engine* e, const Delta& d, int p, int q, const double* Lf, int64_t ldlf, const double* Rf, int64_t ldrf,
                    double* Sout, int64_t lds) {
     Ctx& cx = e->cx;
+    NvtxRange nvtx_pass("dlra:pass_S");
     if (!(e->flags & DLRA_FORCE_GENERIC) && tma_pass_supported(e->n, e->m, d)) {
         tma_pass_S(e, d, p, q, Lf, ldlf, Rf, ldrf, Sout, lds);
         return;
