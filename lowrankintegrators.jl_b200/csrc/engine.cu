@@ -457,7 +457,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     if (pre) {
         // K = ΔA*V0 (already in UB) + U0*S0: the update is folded into the TSQR panel load below
         if (!lfin_aux)
-            l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, h->kl_ldlp * 16, h->V, m, h->S, W, r, L, m);  // L = ΔA'*U0 + V0*S0'
+            l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, 16, 1, h->V, m, h->S, W, r, L, m);  // L = ΔA'*U0 + V0*S0'
     } else {
         gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);
     }
@@ -470,7 +470,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
         de_L_flow(h, L, r, h->U, sc.t, sc.dt);
     }
     fork_aux(h);                                          // m-side chain on the auxiliary stream ...
-    if (lfin_aux) l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, h->kl_ldlp * 16, h->V, m, h->S, W, r, L, m, &h->ax);
+    if (lfin_aux) l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, 16, 1, h->V, m, h->S, W, r, L, m, &h->ax);
     qr_mside(h, aux_side(h), L, r, nullptr);              // V1 = qr(L).Q
     gram_mside(h, aux_side(h), r, r, L, h->V, h->N);      // N = V1'*V0
     if (pre) qr_nside_plus(h, K, r, h->U, h->S, r);       // ... overlaps U1 = qr(ΔA*V0 + U0*S0).Q

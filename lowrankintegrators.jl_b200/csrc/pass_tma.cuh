@@ -27,7 +27,9 @@ constexpr int PT_SI = 64;        // rows per stage
 constexpr int PT_TJ = 32;        // columns per stage
 constexpr int PT_NSUB_MAX = 7;   // stages (row sub-tiles) per panel held in K accumulators
 constexpr int PT_CONSUMERS = 8;  // consumer warps
-constexpr int PT_THREADS = (PT_CONSUMERS + 4) * 32;   // + one service warpgroup: TMA producer warp, L-reducer warp, 2 idle
+constexpr int PT_THREADS = (PT_CONSUMERS + 4) * 32;   // + one service warpgroup: TMA producer warp + three L-reducer warps
+constexpr int PT_NRED = 3;       // reducer warps (one warp alone is starved by the consumers' DMMA stream: its DADDs share the fp64 pipe)
+constexpr int PT_MAX_CLUSTER = 4;  // CTAs of a cluster split the factor columns (16 each) and share every ΔA tile through TMA multicast
 constexpr int PT_LRED_LD = PT_TJ + 2;                 // padded column stride of the L reduction buffer (conflict-free)
 constexpr int PT_TBYTES = PT_SI * PT_TJ * 8;  // 16 KB
 constexpr int PT_BOXBYTES = 16 * PT_TJ * 8;   // 4 KB: one 16-row box
@@ -44,10 +46,12 @@ struct PassParams {
 
 template <int RT, bool DO_K, bool DO_L, bool DIFF>
 struct PassSmem {
+    // row sub-tiles per panel: bounded by the K accumulators a consumer thread can hold next to the L accumulators
+    static constexpr int NSUBM = (RT == 32 && DO_L) ? 3 : PT_NSUB_MAX;
     static constexpr int VBYTES = DO_K ? PT_TJ * RT * 8 : 0;
     static constexpr int STAGE_BYTES = ((PT_TBYTES * (DIFF ? 2 : 1) + VBYTES + 1023) / 1024) * 1024;
     static constexpr int UBOX_BYTES = 16 * RT * 8;
-    static constexpr int UPANEL_BYTES = DO_L ? PT_NSUB_MAX * 4 * UBOX_BYTES : 0;
+    static constexpr int UPANEL_BYTES = DO_L ? NSUBM * 4 * UBOX_BYTES : 0;
     static constexpr int LRED_BYTES = DO_L ? ((PT_CONSUMERS * PT_LRED_LD * RT * 8 + 1023) / 1024) * 1024 : 0;
     static constexpr int BUDGET = 225 * 1024;
     static constexpr int NST_RAW = (BUDGET - UPANEL_BYTES - LRED_BYTES - 1024) / STAGE_BYTES;
@@ -63,6 +67,7 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     constexpr int NST = SM::NST;
     constexpr int NB = RT / 8;
     constexpr int LD = PT_LRED_LD;
+    constexpr int NSUBM = SM::NSUBM;
     extern __shared__ unsigned char smem_dyn[];
     // 1024-byte aligned carve-up (SWIZZLE_128B boxes need it)
     unsigned char* base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
@@ -77,14 +82,22 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     uint64_t* lfree = bars + 2 * NST + 2;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // Thread-block cluster (1..4 CTAs): CTA q owns factor columns [RT*q, RT*q + RT) — its own V tile, U panel, K columns and
+    // L partial — while the ΔA stage is fetched ONCE per cluster: CTA q issues boxes b with b % cl_size == q as multicast
+    // loads that land in every CTA of the cluster.  A stage slot may be refilled only when the consumers of ALL CTAs have
+    // released it, so every consumer warp arrives on the empty barrier of every CTA of the cluster.
+    const uint32_t cl_size = cluster_nctarank(), cl_rank = cluster_ctarank();
+    const int coff = (int)cl_rank * RT;
+    const int nclusters = (int)(gridDim.x / cl_size), cluster_id = (int)(blockIdx.x / cl_size);
     if (tid == 0) {
-        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], PT_CONSUMERS); }
+        for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], PT_CONSUMERS * cl_size); }
         mbar_init(panel_done, PT_CONSUMERS);
         mbar_init(lfull, PT_CONSUMERS);
-        mbar_init(lfree, 1);
+        mbar_init(lfree, PT_NRED);
         mbar_fence_init();
     }
     __syncthreads();
+    if (cl_size > 1) cluster_sync_all();   // every CTA's barriers exist before the first remote arrive / multicast
 
     const int nsub = prm.nsub;
     // register re-partitioning (sm_90+ setmaxnreg): the service warpgroup gives its registers to the two consumer warpgroups
@@ -99,8 +112,9 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
             if (DO_K) prefetch_tmap(&mapV);
             const uint64_t pol_stream = policy_evict_first();
             const uint64_t pol_keep = policy_evict_last();
+            const uint16_t mc_mask = (uint16_t)((1u << cl_size) - 1u);
             int stage = 0; uint32_t phase = 0; uint32_t pd_phase = 0; bool first_panel = true;
-            for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
+            for (int panel = cluster_id; panel < prm.npanels; panel += nclusters) {
                 if (!first_panel) { mbar_wait(panel_done, pd_phase); pd_phase ^= 1; }  // U panel region is free again
                 first_panel = false;
                 const int row0 = panel * nsub * PT_SI;
@@ -113,61 +127,73 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         mbar_expect_tx(&full[stage], bytes);
                         unsigned char* sb = stages + (size_t)stage * SM::STAGE_BYTES;
                         const int r = row0 + s * PT_SI;
+                        if (cl_size == 1) {
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) {
-                            tma_load_2d(sb + b * PT_BOXBYTES, &mapA, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
-                            if (DIFF) tma_load_2d(sb + PT_TBYTES + b * PT_BOXBYTES, &mapP, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
+                            for (int b = 0; b < 4; ++b) {
+                                tma_load_2d(sb + b * PT_BOXBYTES, &mapA, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
+                                if (DIFF) tma_load_2d(sb + PT_TBYTES + b * PT_BOXBYTES, &mapP, r + 16 * b, jt * PT_TJ, &full[stage], pol_stream);
+                            }
+                        } else {
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) {
+                                if ((uint32_t)b % cl_size != cl_rank) continue;   // the peers fetch the other boxes for everybody
+                                tma_load_2d_mc(sb + b * PT_BOXBYTES, &mapA, r + 16 * b, jt * PT_TJ, &full[stage], mc_mask, pol_stream);
+                                if (DIFF) tma_load_2d_mc(sb + PT_TBYTES + b * PT_BOXBYTES, &mapP, r + 16 * b, jt * PT_TJ, &full[stage], mc_mask, pol_stream);
+                            }
                         }
                         if (DO_K && s == 0) {
 #pragma unroll
                             for (int b = 0; b < 2; ++b)
-                                tma_load_2d(sb + PT_TBYTES * (DIFF ? 2 : 1) + b * (16 * RT * 8), &mapV, jt * PT_TJ + 16 * b, 0, &full[stage], pol_keep);
+                                tma_load_2d(sb + PT_TBYTES * (DIFF ? 2 : 1) + b * (16 * RT * 8), &mapV, jt * PT_TJ + 16 * b, coff, &full[stage], pol_keep);
                         }
                         if (DO_L && jt == 0) {
 #pragma unroll
                             for (int b = 0; b < 4; ++b)
-                                tma_load_2d(upanel + (size_t)(s * 4 + b) * SM::UBOX_BYTES, &mapU, r + 16 * b, 0, &full[stage], pol_keep);
+                                tma_load_2d(upanel + (size_t)(s * 4 + b) * SM::UBOX_BYTES, &mapU, r + 16 * b, coff, &full[stage], pol_keep);
                         }
                         if (++stage == NST) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-        return;
-    }
-    if (warp == PT_CONSUMERS + 1) {
-        // ------------------------------ L reducer: sums the 8 consumer warps' partial L tiles off the critical path ---
-        if (DO_L) {
-            uint32_t ph = 0;
-            // one partial per CTA: the first panel stores, later panels of this CTA accumulate (fixed order => deterministic)
-            double* lp = prm.Lpart + (size_t)blockIdx.x * prm.ldlp * RT;
-            for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
-                const bool first = (panel == (int)blockIdx.x);
-                for (int jt = 0; jt < prm.ntj; ++jt) {
-                    const int64_t col = (int64_t)jt * PT_TJ + lane;
-                    const bool okc = col < prm.m;
-                    double prev[RT];
-                    // the previous panels' running sum is fetched BEFORE waiting for the consumers (latency fully hidden)
+    } else if (DO_L) {
+        // ------------------------------ L reducers: three warps sum the 8 consumer warps' partial L tiles off the critical
+        // path; warp wr owns the factor columns i = wr, wr + 3, ... of the tile
+        const int wr = warp - PT_CONSUMERS - 1;
+        constexpr int NI = (RT + PT_NRED - 1) / PT_NRED;
+        uint32_t ph = 0;
+        // one partial per CTA: the first panel stores, later panels of this CTA accumulate (fixed order => deterministic)
+        double* lp = prm.Lpart + (size_t)blockIdx.x * prm.ldlp * RT;
+        for (int panel = cluster_id; panel < prm.npanels; panel += nclusters) {
+            const bool first = (panel == cluster_id);
+            for (int jt = 0; jt < prm.ntj; ++jt) {
+                const int64_t col = (int64_t)jt * PT_TJ + lane;
+                const bool okc = col < prm.m;
+                double prev[NI];
+                // the previous panels' running sum is fetched BEFORE waiting for the consumers (latency fully hidden)
 #pragma unroll
-                    for (int i = 0; i < RT; ++i) prev[i] = (!first && okc) ? __ldcg(lp + col + (int64_t)i * prm.ldlp) : 0.0;
-                    mbar_wait(lfull, ph);
+                for (int q = 0; q < NI; ++q) {
+                    const int i = wr + q * PT_NRED;
+                    prev[q] = (!first && okc && i < RT) ? __ldcg(lp + col + (int64_t)i * prm.ldlp) : 0.0;
+                }
+                mbar_wait(lfull, ph);
 #pragma unroll
-                    for (int i = 0; i < RT; ++i) {   // element (c = i, j = lane)
-                        double sum = prev[i];
+                for (int q = 0; q < NI; ++q) {   // element (c = i, j = lane)
+                    const int i = wr + q * PT_NRED;
+                    if (i < RT) {
+                        double sum = prev[q];
 #pragma unroll
                         for (int w = 0; w < PT_CONSUMERS; ++w) sum += lred[(size_t)w * LD * RT + i * LD + lane];
                         if (okc) __stcg(lp + col + (int64_t)i * prm.ldlp, sum);
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(lfree);
-                    ph ^= 1;
                 }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(lfree);
+                ph ^= 1;
             }
         }
-        return;
     }
-    return;
-    }
+    } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
 
     // ---------------------------------- consumers: 8 warps, DMMA ------------------------------------------
@@ -192,12 +218,12 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
     const int crow = wbox * 16 + prow;
 
     int stage = 0; uint32_t phase = 0; uint32_t lfree_ph = 1;   // first wait on a fresh barrier passes
-    for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
+    for (int panel = cluster_id; panel < prm.npanels; panel += nclusters) {
         const int64_t row0 = (int64_t)panel * nsub * PT_SI;
-        double kacc[PT_NSUB_MAX][NB][2];
+        double kacc[NSUBM][NB][2];
         if (DO_K) {
 #pragma unroll
-            for (int s = 0; s < PT_NSUB_MAX; ++s)
+            for (int s = 0; s < NSUBM; ++s)
 #pragma unroll
                 for (int nb = 0; nb < NB; ++nb) { kacc[s][nb][0] = 0.0; kacc[s][nb][1] = 0.0; }
         }
@@ -211,7 +237,7 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                     for (int nb = 0; nb < NB; ++nb) { lacc[cb][nb][0] = 0.0; lacc[cb][nb][1] = 0.0; }
             }
 #pragma unroll
-            for (int s = 0; s < PT_NSUB_MAX; ++s) {
+            for (int s = 0; s < NSUBM; ++s) {
                 if (s < nsub) {
                     mbar_wait(&full[stage], phase);
                     const unsigned char* sb = stages + (size_t)stage * SM::STAGE_BYTES;
@@ -252,12 +278,15 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         }
                     }
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    if (lane == 0) {
+                        if (cl_size == 1) mbar_arrive(&empty[stage]);
+                        else for (uint32_t q = 0; q < cl_size; ++q) mbar_arrive_remote(&empty[stage], q);
+                    }
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
             if (DO_L) {
-                // hand this warp's partial L tile (32 cols x RT) to the reducer warp
+                // hand this warp's partial L tile (32 cols x RT) to the reducer warps
                 mbar_wait(lfree, lfree_ph);
                 lfree_ph ^= 1;
                 double* mine = lred + (size_t)warp * LD * RT;
@@ -274,7 +303,7 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         }
         if (DO_K) {
 #pragma unroll
-            for (int s = 0; s < PT_NSUB_MAX; ++s) {
+            for (int s = 0; s < NSUBM; ++s) {
                 if (s < nsub) {
                     const int64_t row = row0 + s * PT_SI + crow;
                     if (row < prm.n) {
@@ -282,7 +311,7 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
                         for (int nb = 0; nb < NB; ++nb)
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
-                                const int c = 8 * nb + 2 * k + e;
+                                const int c = coff + 8 * nb + 2 * k + e;
                                 if (c < prm.rc) prm.K[row + (int64_t)c * prm.ldk] += kacc[s][nb][e];
                             }
                     }
@@ -292,6 +321,9 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive(panel_done);
     }
+    }
+    // no CTA may exit while a peer can still multicast into its shared memory or arrive on its barriers
+    if (cl_size > 1) { __syncwarp(); cluster_sync_all(); }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -336,49 +368,124 @@ inline bool tma_pass_supported(int64_t n, int64_t m, const Delta& d) {
     return true;
 }
 
-inline int choose_nsub(int64_t n, int num_sms) {
+// rows per panel = 64·nsub; `workers` = clusters (or CTAs) that sweep panels concurrently
+inline int choose_nsub(int64_t n, int workers, int nsub_max = PT_NSUB_MAX) {
     const int64_t subtiles = cdiv(n, PT_SI);
     int best = 1; double best_cost = 1e300;
-    for (int ns = 1; ns <= PT_NSUB_MAX; ++ns) {
+    for (int ns = 1; ns <= nsub_max; ++ns) {
         const int64_t panels = cdiv(subtiles, ns);
-        const double cost = (double)cdiv(panels, num_sms) * ns + 0.02 * (double)panels / num_sms;  // makespan + partial-L overhead
+        const double cost = (double)cdiv(panels, workers) * ns + 0.02 * (double)panels / workers;  // makespan + partial-L overhead
         if (cost < best_cost - 1e-12) { best_cost = cost; best = ns; }
     }
     return best;
 }
 
+// co-resident clusters of `csize` CTAs for a kernel (depends on the GPC shapes of the part; queried once per device and size)
+template <class Kern>
+inline int max_active_clusters(Kern kern, int csize, int smem_bytes, int num_sms) {
+    if (csize <= 1) return num_sms;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(csize * (num_sms / csize)));
+    cfg.blockDim = dim3(PT_THREADS);
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int ncl = 0;
+    DLRA_CUDA(cudaOccupancyMaxActiveClusters(&ncl, kern, &cfg));
+    DLRA_REQUIRE(ncl >= 1, "the device cannot co-schedule a cluster of this size");
+    return std::min(ncl, num_sms / csize);
+}
+
+// shape of one pass launch: `csize` CTAs per cluster (1 = plain launch), nclusters clusters sweeping the row panels
+struct PassGrid {
+    int csize = 1, nclusters = 1, nsub = 1, npanels = 1;
+    int ctas() const { return csize * nclusters; }
+};
+
+template <int RT, bool DO_K, bool DO_L, bool DIFF>
+inline PassGrid pass_grid(dlra_engine* e, int csize) {
+    using SM = PassSmem<RT, DO_K, DO_L, DIFF>;
+    auto kern = pass_kernel<RT, DO_K, DO_L, DIFF>;
+    static unsigned long long attr_devs = 0;
+    static int cached[64][PT_MAX_CLUSTER + 1] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (first_use_on_this_device(attr_devs))
+        DLRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    DLRA_REQUIRE(csize >= 1 && csize <= PT_MAX_CLUSTER, "cluster size out of range");
+    int& mc = cached[dev & 63][csize];
+    if (mc == 0) {
+        mc = max_active_clusters(kern, csize, SM::TOTAL, e->cx.num_sms);
+        if (getenv("DLRA_DEBUG")) fprintf(stderr, "[dlra] pass_kernel<%d,%d,%d,%d> cluster %d: %d co-resident clusters (%d of %d SMs), %d stages, %d B smem\n",
+                                          RT, (int)DO_K, (int)DO_L, (int)DIFF, csize, mc, mc * csize, e->cx.num_sms, SM::NST, SM::TOTAL);
+    }
+    PassGrid g;
+    g.csize = csize;
+    g.nsub = choose_nsub(e->n, mc, SM::NSUBM);
+    g.npanels = (int)cdiv(cdiv(e->n, PT_SI), g.nsub);
+    g.nclusters = std::min(g.npanels, mc);
+    return g;
+}
+
+// one launch: factor columns [0, rc) of Vf / Uf / K, RT per CTA, g.csize >= ceil(rc / RT) CTAs per cluster.
+// Lpart: g.ctas() partials of ldlp x RT doubles; the partials of the factor columns [RT*q, RT*q + RT) are those of the CTAs
+// with rank q in their cluster, i.e. blocks q, q + csize, q + 2*csize, ...
 template <int RT, bool DO_K, bool DO_L, bool DIFF>
 inline void launch_pass(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
-                        double* K, int64_t ldk, double* Lpart, int64_t ldlp, int nsub, int npanels) {
+                        double* K, int64_t ldk, double* Lpart, int64_t ldlp, const PassGrid& g) {
     using SM = PassSmem<RT, DO_K, DO_L, DIFF>;
     static_assert(SM::NST >= 2, "pipeline needs at least two stages");
     auto kern = pass_kernel<RT, DO_K, DO_L, DIFF>;
-    static unsigned long long attr_devs = 0;
-    if (first_use_on_this_device(attr_devs))
-        DLRA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     CUtensorMap mapA = make_map_2d(d.A, e->n, e->m, d.lda, 16, PT_TJ, true);
     CUtensorMap mapP = DIFF ? make_map_2d(d.Aprev, e->n, e->m, d.ldap, 16, PT_TJ, true) : mapA;
     CUtensorMap mapU = DO_L ? make_map_2d(Uf, e->n, rc, ldu, 16, RT, true) : mapA;
     CUtensorMap mapV = DO_K ? make_map_2d(Vf, e->m, rc, ldv, 16, RT, true) : mapA;
     PassParams prm;
-    prm.n = e->n; prm.m = e->m; prm.rc = rc; prm.nsub = nsub; prm.npanels = npanels; prm.ntj = (int)cdiv(e->m, PT_TJ);
+    prm.n = e->n; prm.m = e->m; prm.rc = rc; prm.nsub = g.nsub; prm.npanels = g.npanels; prm.ntj = (int)cdiv(e->m, PT_TJ);
     prm.K = K; prm.ldk = ldk; prm.Lpart = Lpart; prm.ldlp = ldlp;
-    const int grid = std::min(npanels, e->cx.num_sms);
     const double bytes = (double)e->n * (double)e->m * 8.0 * (DIFF ? 2.0 : 1.0);
     const double flops = 2.0 * (double)e->n * (double)e->m * rc * ((DO_K ? 1 : 0) + (DO_L ? 1 : 0));
     pass_timer_begin(e, bytes, (DO_K && DO_L) ? 0 : (DO_K ? 1 : 2), flops);
-    kern<<<grid, PT_THREADS, SM::TOTAL, e->cx.stream>>>(mapA, mapP, mapU, mapV, prm);
+    if (g.csize == 1) {
+        kern<<<g.ctas(), PT_THREADS, SM::TOTAL, e->cx.stream>>>(mapA, mapP, mapU, mapV, prm);
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)g.ctas());
+        cfg.blockDim = dim3(PT_THREADS);
+        cfg.dynamicSmemBytes = SM::TOTAL;
+        cfg.stream = e->cx.stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)g.csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        DLRA_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapP, mapU, mapV, prm));
+    }
     pass_timer_end(e);
     e->cx.launches++;
     DLRA_CUDA(cudaGetLastError());
 }
 
+// runtime (K?, L?, DIFF?) -> template instance
+template <int RT>
+inline PassGrid pass_grid_rt(dlra_engine* e, bool dk, bool dl, bool df, int csize) {
+#define DLRA_PASS_CASE(a, b, c) if (dk == a && dl == b && df == c) return pass_grid<RT, a, b, c>(e, csize);
+    DLRA_PASS_CASE(true, true, false)
+    DLRA_PASS_CASE(true, true, true)
+    DLRA_PASS_CASE(true, false, false)
+    DLRA_PASS_CASE(true, false, true)
+    DLRA_PASS_CASE(false, true, false)
+    DLRA_PASS_CASE(false, true, true)
+#undef DLRA_PASS_CASE
+    throw CudaError(1, "pass without outputs");
+}
 template <int RT>
 inline void launch_pass_rt(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
-                           double* K, int64_t ldk, double* Lpart, int64_t ldlp, int nsub, int npanels) {
+                           double* K, int64_t ldk, double* Lpart, int64_t ldlp, const PassGrid& g) {
     const bool dk = K != nullptr, dl = Lpart != nullptr, df = d.Aprev != nullptr;
 #define DLRA_PASS_CASE(a, b, c) \
-    if (dk == a && dl == b && df == c) return launch_pass<RT, a, b, c>(e, d, rc, Vf, ldv, Uf, ldu, K, ldk, Lpart, ldlp, nsub, npanels);
+    if (dk == a && dl == b && df == c) return launch_pass<RT, a, b, c>(e, d, rc, Vf, ldv, Uf, ldu, K, ldk, Lpart, ldlp, g);
     DLRA_PASS_CASE(true, true, false)
     DLRA_PASS_CASE(true, true, true)
     DLRA_PASS_CASE(true, false, false)
@@ -394,11 +501,11 @@ inline void launch_pass_rt(dlra_engine* e, const Delta& d, int rc, const double*
 // sequence flag in every peer, then all CTAs wait for the peers' flags and add the peers' slices in rank order.
 template <bool XR>
 __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int nparts, const double* __restrict__ part, int64_t ldlp,
-                                                         int64_t part_stride, const double* __restrict__ Vi, int64_t ldvi,
+                                                         int64_t part_stride, int rt, const double* __restrict__ Vi, int64_t ldvi,
                                                          const double* __restrict__ Si, int64_t ldsi, int rk, double* __restrict__ L,
-                                                         int64_t ldl, P2PView v, unsigned int* ticket) {
-    extern __shared__ double Ss[];   // [rc][rk]
-    if (Vi) {
+                                                         int64_t ldl, P2PView v, unsigned int* ticket, int s_in_smem) {
+    extern __shared__ double Ss[];   // [rc][rk] (when it fits the default dynamic shared memory; else S is read through the cache)
+    if (Vi && s_in_smem) {
         for (int e = threadIdx.x; e < rc * rk; e += blockDim.x) Ss[e] = Si[(e / rk) + (int64_t)(e % rk) * ldsi];
     }
     __syncthreads();
@@ -407,8 +514,12 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
     auto init_term = [&](int64_t j, int c) {
         double t = 0.0;
         if (Vi) {
-            const double* sr = Ss + c * rk;
-            for (int k = 0; k < rk; ++k) t = fma(Vi[j + (int64_t)k * ldvi], sr[k], t);
+            if (s_in_smem) {
+                const double* sr = Ss + c * rk;
+                for (int k = 0; k < rk; ++k) t = fma(Vi[j + (int64_t)k * ldvi], sr[k], t);
+            } else {
+                for (int k = 0; k < rk; ++k) t = fma(Vi[j + (int64_t)k * ldvi], __ldg(Si + c + (int64_t)k * ldsi), t);
+            }
         }
         return t;
     };
@@ -416,7 +527,8 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
         const int64_t j = e % m;
         const int c = (int)(e / m);
         double s = 0.0;
-        const double* pp = part + j + (int64_t)c * ldlp;
+        // factor column c lives in the partial of cluster rank c / rt (rt columns per CTA), local column c % rt
+        const double* pp = part + (int64_t)(c / rt) * ldlp * rt + j + (int64_t)(c % rt) * ldlp;
 #pragma unroll 8
         for (int p = 0; p < nparts; ++p) s += pp[(int64_t)p * part_stride];
         if (XR) v.data_local[e] = s;
@@ -445,9 +557,11 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
     }
 }
 
-// Lout chunk (m x rc) = Σ_parts (+ Σ_ranks) + Vi·Siᵀ ; picks the fused kernel when it can (single GPU or P2P transport)
-inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, int64_t ldlp, int64_t part_stride, const double* Vi,
+// Lout chunk (m x rc) = Σ_parts (+ Σ_ranks) + Vi·Siᵀ ; picks the fused kernel when it can (single GPU or P2P transport).
+// Partials come from a pass launched with `rt` factor columns per CTA and `csize` CTAs per cluster, `nparts` clusters.
+inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, int64_t ldlp, int rt, int csize, const double* Vi,
                        int64_t ldvi, const double* Si, int64_t ldsi, int rk, double* L, int64_t ldl, Ctx* on = nullptr) {
+    const int64_t part_stride = ldlp * rt * csize;
     Ctx& cx = on ? *on : e->cx;   // single-GPU runs may place this L-side kernel on the auxiliary stream
     Comm& cm = e->comm;
     DLRA_REQUIRE(on == nullptr || cm.nranks <= 1, "collectives stay on the main stream");
@@ -455,18 +569,21 @@ inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, i
     // the cross-rank variant spins on peer flags, so its whole grid must be co-resident (256 threads, <= 16 KB smem: >= 4 CTAs/SM)
     const bool xr = cm.nranks > 1 && cm.p2p;
     const int grid = (int)std::min<int64_t>(cdiv(total, 256), xr ? 4 * (int64_t)cx.num_sms : ((int64_t)1 << 30));
-    const size_t smem = Vi ? (size_t)rc * rk * sizeof(double) : 0;
+    const int s_in_smem = (size_t)rc * rk * sizeof(double) <= 40 * 1024 ? 1 : 0;
+    const size_t smem = (Vi && s_in_smem) ? (size_t)rc * rk * sizeof(double) : 0;
     if (cm.nranks <= 1) {
-        l_finalize_kernel<false><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, Vi, ldvi, Si, ldsi, rk, L, ldl, P2PView{}, nullptr);
+        l_finalize_kernel<false><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, P2PView{}, nullptr, s_in_smem);
         cx.launches++;
     } else if (cm.p2p) {
         DLRA_REQUIRE((size_t)total * 8 <= cm.xdata_bytes, "P2P exchange region too small for an L chunk");
         P2PView v = cm.next_view();
-        l_finalize_kernel<true><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, Vi, ldvi, Si, ldsi, rk, L, ldl, v, cm.ticket);
+        l_finalize_kernel<true><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, v, cm.ticket, s_in_smem);
         cx.launches++;
     } else {
         // NCCL transport: local reduction, library all-reduce of the dense chunk (ldl == m), then the initial term
-        reduce_parts(cx, (int)e->m, rc, nparts, part, ldlp, part_stride, L, ldl, 1.0, 0.0);
+        for (int q = 0; q * rt < rc; ++q)
+            reduce_parts(cx, (int)e->m, std::min(rt, rc - q * rt), nparts, part + (int64_t)q * ldlp * rt, ldlp, part_stride,
+                         L + (int64_t)q * rt * ldl, ldl, 1.0, 0.0);
         if (ldl == e->m) cm.allreduce_sum(L, total, cx);
         else for (int c = 0; c < rc; ++c) cm.allreduce_sum(L + (int64_t)c * ldl, e->m, cx);
         if (Vi) gemm_nn(cx, e->m, rk, rc, Vi, ldvi, nullptr, 0, Si, ldsi, true, L, ldl, 1.0, 1.0);
@@ -474,45 +591,49 @@ inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, i
     DLRA_CUDA(cudaGetLastError());
 }
 
-// K-only launches also exist with 32 factor columns per chunk (K accumulators + V fragments still fit the register file):
-// at r = 32 a K-only pass is HBM-bound again, so one sweep instead of two halves its time.
-inline void launch_pass_k32(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, double* K, int64_t ldk, int nsub,
-                            int npanels) {
-    if (d.Aprev) launch_pass<32, true, false, true>(e, d, rc, Vf, ldv, nullptr, 0, K, ldk, nullptr, 0, nsub, npanels);
-    else launch_pass<32, true, false, false>(e, d, rc, Vf, ldv, nullptr, 0, K, ldk, nullptr, 0, nsub, npanels);
+// tuning knobs for A/B runs on hardware (read once): DLRA_MAX_CLUSTER = 1..4 CTAs per cluster (1 restores one sweep per 16
+// factor columns), DLRA_KONLY_RT = 16 | 32 factor columns per CTA in K-only sweeps wider than 16 columns
+inline int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    const int v = atoi(s);
+    return v < lo ? lo : (v > hi ? hi : v);
 }
+// measured on B200 (profiles/wide_rank_r02.txt): pairs use all 148 SMs (74 co-resident clusters); clusters of 4 leave ~10 % of the SMs idle
+inline int pass_max_cluster() { static int v = env_int("DLRA_MAX_CLUSTER", 2, 1, PT_MAX_CLUSTER); return v; }
+inline int pass_konly_rt() { static int v = env_int("DLRA_KONLY_RT", 32, 16, 32); return v >= 32 ? 32 : 16; }
+inline int pass_fused_rt() { static int v = env_int("DLRA_FUSED_RT", 16, 16, 32); return v >= 32 ? 32 : 16; }
 
-// K (n x r) += ΔA·Vf and/or Lout (m x r, ldl) = ΔAᵀ·Uf, r processed in chunks of 16 (8 for a narrow tail)
+// K (n x r) += ΔA·Vf and/or Lout (m x r, ldl) = ΔAᵀ·Uf.  One sweep over ΔA covers up to 32·C factor columns: a cluster of
+// up to C CTAs, 16 or 32 columns each, shares every ΔA tile through TMA multicast; wider blocks take several sweeps.
 // Lout is COMPLETE on return: summed over this rank's panels, over the ranks of a row-sharded run, plus Vi·Siᵀ if given.
 inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
                         double* K, int64_t ldk, double* Lout, int64_t ldl, const double* Vi = nullptr, int64_t ldvi = 0,
                         const double* Si = nullptr, int64_t ldsi = 0) {
     // factor operands must satisfy the TMA alignment rules too; otherwise stage them through aligned scratch
     DLRA_REQUIRE((!K || tma_ok(Vf, ldv)) && (!Lout || tma_ok(Uf, ldu)), "factor buffers must be 16-byte aligned with even ld");
-    const int nsub = choose_nsub(e->n, e->cx.num_sms);
-    const int npanels = (int)cdiv(cdiv(e->n, PT_SI), nsub);
     const int64_t ldlp = round_up(e->m, 2);
-    const int nparts = std::min(npanels, e->cx.num_sms);   // == grid size of the pass kernel
-    if (Lout) e->part.ensure((int64_t)nparts * ldlp * 16, e->cx.stream);
+    const bool dk = K != nullptr, dl = Lout != nullptr, df = d.Aprev != nullptr;
+    const int maxc = pass_max_cluster();
     for (int c0 = 0; c0 < r;) {
-        if (K && !Lout && r - c0 > 16) {   // wide K-only chunk
-            const int rc32 = std::min(32, r - c0);
-            launch_pass_k32(e, d, rc32, Vf + (int64_t)c0 * ldv, ldv, K + (int64_t)c0 * ldk, ldk, nsub, npanels);
-            c0 += rc32;
-            continue;
-        }
-        const int rc = std::min(16, r - c0);
+        const int rem = r - c0;
         double* Kc = K ? K + (int64_t)c0 * ldk : nullptr;
-        double* Lp = Lout ? e->part.p : nullptr;
         const double* Vc = Vf ? Vf + (int64_t)c0 * ldv : nullptr;
         const double* Uc = Uf ? Uf + (int64_t)c0 * ldu : nullptr;
-        if (rc <= 8) {
-            launch_pass_rt<8>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
-            if (Lout) l_finalize(e, rc, nparts, Lp, ldlp, ldlp * 8, Vi, ldvi, Si ? Si + c0 : nullptr, ldsi, r, Lout + (int64_t)c0 * ldl, ldl);
-        } else {
-            launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, nsub, npanels);
-            if (Lout) l_finalize(e, rc, nparts, Lp, ldlp, ldlp * 16, Vi, ldvi, Si ? Si + c0 : nullptr, ldsi, r, Lout + (int64_t)c0 * ldl, ldl);
-        }
+        const int rt = rem <= 8 ? 8 : (rem <= 16 ? 16 : ((dk && !dl) ? pass_konly_rt() : pass_fused_rt()));
+        const int csize = std::min(maxc, (int)cdiv(rem, rt));
+        const int rc = std::min(rem, rt * csize);
+        PassGrid g;
+        if (rt == 8) g = pass_grid_rt<8>(e, dk, dl, df, csize);
+        else if (rt == 16) g = pass_grid_rt<16>(e, dk, dl, df, csize);
+        else g = pass_grid_rt<32>(e, dk, dl, df, csize);
+        if (dl) e->part.ensure((int64_t)g.ctas() * ldlp * rt, e->cx.stream);
+        double* Lp = dl ? e->part.p : nullptr;
+        if (rt == 8) launch_pass_rt<8>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g);
+        else if (rt == 16) launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g);
+        else launch_pass_rt<32>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g);
+        // CTA q of every cluster holds the partial of the factor columns [rt*q, rt*q + rt)
+        if (dl) l_finalize(e, rc, g.nclusters, Lp, ldlp, rt, csize, Vi, ldvi, Si ? Si + c0 : nullptr, ldsi, r, Lout + (int64_t)c0 * ldl, ldl);
         c0 += rc;
     }
 }

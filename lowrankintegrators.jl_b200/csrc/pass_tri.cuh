@@ -60,7 +60,7 @@ tri_pass_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant_
     if (tid == 0) {
         for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], PT_CONSUMERS); }
         mbar_init(lfull, PT_CONSUMERS);
-        mbar_init(lfree, 1);
+        mbar_init(lfree, PT_NRED);
         mbar_fence_init();
     }
     __syncthreads();
@@ -102,7 +102,9 @@ tri_pass_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant_
             }
             return;
         }
-        if (warp == PT_CONSUMERS + 1) {
+        {   // three reducer warps: warp wr owns the factor columns i = wr, wr + 3, ... (see pass_tma.cuh)
+            const int wr = warp - PT_CONSUMERS - 1;
+            constexpr int NI = (RT + PT_NRED - 1) / PT_NRED;
             uint32_t ph = 0;
             double* lp = prm.Lpart + (size_t)blockIdx.x * prm.ldlp * RT;
             for (int panel = blockIdx.x; panel < prm.npanels; panel += gridDim.x) {
@@ -110,16 +112,22 @@ tri_pass_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant_
                 for (int jt = 0; jt < prm.ntj; ++jt) {
                     const int64_t col = (int64_t)jt * PT_TJ + lane;
                     const bool okc = col < prm.m;
-                    double prev[RT];
+                    double prev[NI];
 #pragma unroll
-                    for (int i = 0; i < RT; ++i) prev[i] = (!first && okc) ? __ldcg(lp + col + (int64_t)i * prm.ldlp) : 0.0;
+                    for (int q = 0; q < NI; ++q) {
+                        const int i = wr + q * PT_NRED;
+                        prev[q] = (!first && okc && i < RT) ? __ldcg(lp + col + (int64_t)i * prm.ldlp) : 0.0;
+                    }
                     mbar_wait(lfull, ph);
 #pragma unroll
-                    for (int i = 0; i < RT; ++i) {
-                        double sum = prev[i];
+                    for (int q = 0; q < NI; ++q) {
+                        const int i = wr + q * PT_NRED;
+                        if (i < RT) {
+                            double sum = prev[q];
 #pragma unroll
-                        for (int w = 0; w < PT_CONSUMERS; ++w) sum += lred[(size_t)w * LD * RT + i * LD + lane];
-                        if (okc) __stcg(lp + col + (int64_t)i * prm.ldlp, sum);
+                            for (int w = 0; w < PT_CONSUMERS; ++w) sum += lred[(size_t)w * LD * RT + i * LD + lane];
+                            if (okc) __stcg(lp + col + (int64_t)i * prm.ldlp, sum);
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(lfree);
@@ -128,7 +136,6 @@ tri_pass_kernel(const __grid_constant__ CUtensorMap map2, const __grid_constant_
             }
             return;
         }
-        return;
     }
     asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
 

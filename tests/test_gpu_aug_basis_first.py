@@ -1,17 +1,14 @@
 """Rank-adaptive step with the augmented bases factored as [U0 | K], [V0 | L] (DLRA_AUG_BASIS_FIRST): same span as the
 reference's [K | U0], [L | V0], hence the same U·S·Vᵀ and the same selected ranks, with one TSQR less per side.
 
-Written after the round-1 GPU budget was spent: NOT YET RUN ON HARDWARE, therefore opt-in (DLRA_UNVALIDATED=1)."""
-import os
-
+Validated on a B200 at the start of round 2 (16 cases green, gpurun_out/r2_base/pytest_optin.txt)."""
 import numpy as np
 import pytest
 
 from oracle import dlra_oracle as O
 from tests.problems import lowrank_stream, rel_fro
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DLRA_UNVALIDATED") != "1", reason="DLRA_AUG_BASIS_FIRST: not validated on hardware yet")]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("n,m,r,R", [(4096, 512, 16, 20), (2048, 384, 6, 10), (4096, 256, 24, 30), (2050, 130, 5, 8)])

@@ -1,10 +1,7 @@
 """GPU parity of right-hand sides with two-sided terms F(X) = Σ_k A_k·X·B_kᵀ (dlra_rhs_add_term) against the CPU oracle:
 random dense terms for every integrator and the chemical master equation of examples/markov_chain.jl at reduced size.
 
-Written after the round-1 GPU budget was spent: NOT YET RUN ON HARDWARE, therefore opt-in (DLRA_UNVALIDATED=1) so that an
-untested path cannot turn the suite red; enable it first thing when a GPU is available."""
-import os
-
+Validated on a B200 at the start of round 2 (16 cases green, gpurun_out/r2_base/pytest_optin.txt)."""
 import numpy as np
 import pytest
 import scipy.sparse as sp
@@ -13,8 +10,7 @@ from oracle import dlra_oracle as O
 from tests.problems import cme_operators, rel_fro
 from tests.test_gpu_de_parity import algs, csr_dev, dev, run_both
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("DLRA_UNVALIDATED") != "1", reason="two-sided terms: not validated on hardware yet")]
+pytestmark = pytest.mark.gpu
 TOL = 1e-10
 
 
