@@ -8,7 +8,11 @@ Workload (N=1): BASELINE.json configs[1] — MatrixDataProblem synthetic snapsho
 unconventional (BUG) integrator.  A "step" is one `step!` of the integrator on the next snapshot of a device-resident
 ring; the increment ΔA = A_{k+1} − A_k is formed on the fly inside both streaming passes (the reference's a2 work).
 N>1: every rank holds a cfg-2 sized row shard (n_local = 65536) of an N·65536 x 4096 problem (row sharding of SURVEY.md
-§8e: NCCL all-reduce of L/S/M, all-gather of the TSQR R factors); value counts shard-steps so N=1 equals configs[1].
+§8e: all-reduce of L/S/M, all-gather of the TSQR R factors); `value` counts SHARD-steps/s (weak scaling, N=1 equals
+configs[1]); `steps_per_sec_global` is the step rate of the N·65536-row problem.
+Every line also carries `cfg5_strong`: BASELINE configs[4] (n = 2^22, m = 4096, r = 64, BUG, pre-differenced stream generated
+on the device) row-sharded over the N GPUs with the GLOBAL size fixed — the north star's strong-scaling measurement
+(N=1 holds the single 128 GiB buffer).  --no-cfg5 skips it.
 """
 import argparse
 import json
@@ -23,6 +27,8 @@ sys.path.insert(0, ROOT)
 
 N_ROWS, M_COLS, RANK = 65536, 4096, 16
 METRIC, UNIT = "dlra_steps_per_sec", "steps/s"
+CFG5_N, CFG5_M, CFG5_R = 1 << 22, 4096, 64
+FP64_TFLOPS_FALLBACK = 37.1   # measured DMMA.8x8x4 peak on this pool's B200 (profiles/microbench_r01.json)
 
 
 def measured_peaks():
@@ -31,6 +37,14 @@ def measured_peaks():
             return json.load(f), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def fp64_peak_tflops():
+    try:
+        with open(os.path.join(ROOT, "profiles", "microbench_r01.json")) as f:
+            return float(json.load(f)["dmma884_tflops_8acc_8w_x4cta"]), "measured DMMA.8x8x4 (profiles/microbench_r01.json, tools/microbench.cu)"
+    except Exception:
+        return FP64_TFLOPS_FALLBACK, "measured DMMA.8x8x4 (round 1)"
 
 
 def config_dict(n_gpus, impl):
@@ -72,30 +86,42 @@ def cpu_oracle_steps(n, m, r, steps, warmup):
     return (time.perf_counter() - t0) / steps
 
 
-def blas_threads():
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm is meant to use all the host threads it can, so the
+    BLAS pool is resized at run time.  Returns the thread count actually in effect."""
+    want = os.cpu_count() or 1
     try:
-        from threadpoolctl import threadpool_info
+        from threadpoolctl import threadpool_limits, threadpool_info
+        threadpool_limits(limits=want)
         return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
     except Exception:
-        return os.cpu_count() or 1
+        return 1
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    frac = 8
+    cores = use_all_host_threads()
+    # One warm step at the full shard size tells whether K full-size steps fit the time box (~150 s); if not, each timed
+    # step is a 1/frac row slice (the BUG step is linear in n) and the time is scaled back — said in `sample`.
+    frac = max(1, N_ROWS // args.ref_rows) if args.ref_rows else 1
+    t_full = cpu_oracle_steps(N_ROWS // frac, M_COLS, RANK, 1, 1) * frac
+    while (args.steps + args.warmup) * t_full / frac > 150.0 and frac < 16:
+        frac *= 2
     n_s = N_ROWS // frac
-    sec = cpu_oracle_steps(n_s, M_COLS, RANK, args.steps, args.warmup) * frac   # BUG step cost is linear in n
+    sec = cpu_oracle_steps(n_s, M_COLS, RANK, args.steps, args.warmup) * frac
     value = 1.0 / sec
-    cores = blas_threads()
-    sample = (f"NumPy/OpenBLAS restatement of the reference BUG step (oracle/dlra_oracle.py), each timed step on a "
-              f"{n_s}x{M_COLS} row slice (1/{frac} of the workload), time scaled x{frac} (cost linear in n); "
-              f"Julia reference not runnable (no Julia in the image)")
+    sample = (f"NumPy/OpenBLAS restatement of the reference BUG step (oracle/dlra_oracle.py; the Julia reference is not runnable: "
+              f"no Julia in the image), {args.steps} timed steps on a {n_s}x{M_COLS} r={RANK} stream"
+              + ("" if frac == 1 else f" (1/{frac} row slice of the shard, time scaled x{frac}: the step is linear in n)")
+              + f"; value is in SHARD-steps/s like the GPU arm's: a CPU stepping the {args.gpus}x{N_ROWS}-row problem takes "
+                f"{args.gpus}x as long per global step, so shard-steps/s does not depend on N")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus, "reference-cpu-port"),
+        "steps_per_sec_global": value / args.gpus,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -149,6 +175,90 @@ class ClockSampler:
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": []}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+def cfg5_strong(args, lri, torch, dist, world, rank, local_rank, dev):
+    """BASELINE configs[4]: n = 2^22, m = 4096, r = 64, BUG, pre-differenced increment stream resident in HBM, GLOBAL size
+    fixed and row-sharded over the N ranks (strong scaling).  The global matrix is the same for every N: it is generated in
+    2^19-row blocks, block b from the seed 5000 + b, and rank g owns blocks [8g/N, 8(g+1)/N).  Returns the sub-record."""
+    L = lri._lib
+    n_glob, m, r = CFG5_N, CFG5_M, CFG5_R
+    nblk = 8
+    brows = n_glob // nblk
+    n = n_glob // world
+    need = n * m * 8 + 6 * n * r * 8 + (2 << 30)
+    free, total = torch.cuda.mem_get_info(dev)
+    if free < need:
+        return {"skipped": f"needs {need / 2**30:.1f} GiB on the device, {free / 2**30:.1f} GiB free"}
+    dA = lri.empty_colmajor(n, m, dev)
+    U0 = torch.empty((r, n), device=dev, dtype=torch.float64).t()
+    for lb in range(nblk // world):
+        b = rank * (nblk // world) + lb
+        g = torch.Generator(device=dev)
+        g.manual_seed(5000 + b)
+        rows = slice(lb * brows, (lb + 1) * brows)
+        for j0 in range(0, m, 256):
+            dA[rows, j0:j0 + 256] = (torch.rand((256, brows), generator=g, device=dev, dtype=torch.float64) - 0.5).t()
+        U0[rows] = torch.linalg.qr(torch.randn((brows, r), generator=g, device=dev, dtype=torch.float64))[0] / np.sqrt(nblk)
+    gw = torch.Generator(device=dev)
+    gw.manual_seed(77)
+    V0 = torch.linalg.qr(torch.randn((m, r), generator=gw, device=dev, dtype=torch.float64))[0]
+    S0 = torch.diag(2.0 ** -(0.25 * torch.arange(r, device=dev, dtype=torch.float64)))
+    eng = lri.Engine(n, m, r, rmax=r, device=local_rank)
+    transport = lri.attach_engine(eng) if world > 1 else None
+    eng.set_factors(U0, S0, V0)
+    del U0
+    K5, W5 = args.cfg5_steps, 2
+
+    def step():
+        eng.data_push(dA, L.DATA_DELTA)
+        eng.step_bug()
+
+    for _ in range(W5):
+        step()
+    eng.sync()
+    eng.set_profiling(True)
+    eng.stats(reset=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    eng.event_record(0)
+    for _ in range(K5):
+        step()
+    eng.event_record(1)
+    ms_total = eng.event_elapsed_ms(0, 1)
+    eng.sync()
+    st = eng.stats()
+    brk = eng.pass_breakdown()
+    _, S1, _ = eng.get_factors_device()
+    finite = bool(torch.isfinite(S1).all())
+    eng.close()
+    del dA
+    torch.cuda.empty_cache()
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms = ms_total / K5
+    peaks, _ = measured_peaks()
+    tf_peak, tf_src = fp64_peak_tflops()
+    flops = 6.0 * n * m * r            # per GPU per step (SURVEY.md §8d: BUG 6nmr)
+    abytes = 2.0 * 8.0 * n * m         # two passes over the pre-differenced shard
+    t_fp64, t_hbm = flops / (tf_peak * 1e12) * 1e3, abytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+    bound_ms = max(t_fp64, t_hbm)
+    pass_ms = st["pass_ms"] / K5
+    return {
+        "workload": f"BASELINE configs[4]: n=2^22 (global, fixed), m={m}, r={r}, BUG, pre-differenced stream in HBM, row-sharded x{world}",
+        "scaling": "strong", "n_global": n_glob, "n_local": n, "m": m, "r": r, "steps": K5, "warmup": W5,
+        "ms_per_step": ms, "steps_per_sec": 1e3 / ms, "transport": transport, "finite": finite,
+        "kernels_per_step": st["kernel_launches"] / K5,
+        "roofline": {"bound": "fp64", "flops_per_step_per_gpu": flops, "bytes_per_step_per_gpu": abytes,
+                     "t_fp64_ms": t_fp64, "t_hbm_ms": t_hbm, "achieved_tflops": flops / (ms * 1e-3) / 1e12, "peak_tflops": tf_peak,
+                     "frac": bound_ms / ms, "pass_ms_per_step": pass_ms, "pass_frac": bound_ms / pass_ms if pass_ms > 0 else None,
+                     "ceiling_steps_per_sec": 1e3 / bound_ms, "peak_source": tf_src,
+                     "passes": {k: {"ms_per_launch": v["ms"] / v["launches"], "launches_per_step": v["launches"] / K5,
+                                    "tflops": v["flops"] / (v["ms"] * 1e-3) / 1e12} for k, v in brk.items() if v["launches"] > 0}},
+    }
 
 
 def run_gpu(args):
@@ -269,6 +379,18 @@ def run_gpu(args):
     e2e = {"value": world / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": n * m * 8, "d2h_bytes_per_step": (n * r + r * r + m * r) * 8,
            "steps": Ke, "note": "dlra_data_push_host (pinned host snapshot) + dlra_step_bug + dlra_get_factors_host per step"}
     eng.close()
+    del hsnaps, U0
+    torch.cuda.empty_cache()
+
+    # ---- north-star strong-scaling record (all ranks take part)
+    cfg5 = None
+    if not args.no_cfg5:
+        try:
+            cfg5 = cfg5_strong(args, lri, torch, dist if world > 1 else None, world, rank, local_rank, dev)
+        except Exception as ex:   # the headline numbers above stay valid
+            if world > 1:
+                raise
+            cfg5 = {"error": f"{type(ex).__name__}: {ex}"}
 
     if rank != 0:
         if world > 1:
@@ -298,12 +420,28 @@ def run_gpu(args):
                                      "ms_per_launch": (v["ms"] / v["launches"]) if v["launches"] else None,
                                      "launches": v["launches"]} for k, v in brk.items() if v is not fk and v["launches"] > 0},
                 "pass_share_of_step": st["pass_ms"] / ms_total}
+        # algorithmic bytes = 2 passes x 8·n·m (pre-differenced stream), flops = 6·n·m·r; the bound is
+        # max(t_HBM, t_FP64).  The engine reads 24 B/element because ΔA is formed from three resident snapshots on the
+        # fly (the reference's update_data! work, a2) — `frac` above is against the bytes actually required for that,
+        # the fractions below are against the survey's ceiling.
+        tf_peak, tf_src = fp64_peak_tflops()
+        abytes, aflops = 2.0 * 8.0 * n * m, 6.0 * n * m * r
+        t_hbm, t_fp64 = abytes / (peaks["hbm_gbs"] * 1e9) * 1e3, aflops / (tf_peak * 1e12) * 1e3
+        bound_ms = max(t_hbm, t_fp64)
+        kern_ms = st["pass_ms"] / K
+        roof["algorithmic"] = {"bytes_per_step": abytes, "flops_per_step": aflops, "t_hbm_ms": t_hbm, "t_fp64_ms": t_fp64,
+                               "bound": "fp64" if t_fp64 >= t_hbm else "hbm", "bound_ms": bound_ms,
+                               "fp64_peak_tflops": tf_peak, "fp64_peak_source": tf_src,
+                               "kernel_frac": bound_ms / kern_ms, "step_frac": bound_ms / ms_per_step,
+                               "ceiling_steps_per_sec": 1e3 / bound_ms,
+                               "moved_over_algorithmic_bytes": (fk["bytes"] / fk["launches"]) * (st["pass_launches"] / K) / abytes}
 
     # ---- CPU baseline (rank 0, N=1 only): 2 oracle BUG steps at the full cfg-2 size
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
+        cores = use_all_host_threads()
         sec = cpu_oracle_steps(n, m, r, 2, 1)
-        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"2 timed + 1 warm-up BUG steps of oracle/dlra_oracle.py (NumPy/OpenBLAS restatement of the reference step) at the full {n}x{m}, r={r} size"}
 
     line = {
@@ -311,6 +449,8 @@ def run_gpu(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_dict(world, "libdlra.so"), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": gpu_launches, "clocks": clocks,
+        "value_counts": "shard-steps/s: N cfg-2 shards stepped together (weak scaling); at N=1 this is configs[1] itself",
+        "steps_per_sec_global": 1e3 / ms_per_step, "cfg5_strong": cfg5,
     }
     print(json.dumps(line))
     if world > 1:
@@ -324,6 +464,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-rows", type=int, default=0, help="reference arm: rows of the timed slice (default: the full shard if it fits the time box)")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the configs[4] strong-scaling sub-record")
+    ap.add_argument("--cfg5-steps", type=int, default=5)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

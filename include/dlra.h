@@ -33,7 +33,9 @@ enum {
     DLRA_ENCCL = 3,      /* NCCL failure or NCCL not loadable */
     DLRA_ESTATE = 4,     /* call sequence error (e.g. step without pushed data / without rhs) */
     DLRA_ENOMEM = 5,
-    DLRA_EUNSUPPORTED = 6
+    DLRA_EUNSUPPORTED = 6,
+    DLRA_EMAXITERS = 7   /* adaptive sub-stepper hit its maxiters (OrdinaryDiffEq would return retcode MaxIters); the factors and
+                          * the controller state are those before the failed step */
 };
 
 /* dlra_create flags */
@@ -105,6 +107,13 @@ int dlra_get_factors_host(dlra_handle h, double* U, int64_t ldu, double* S, int6
                           int64_t ldv, int* r);
 int dlra_get_factors(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V,
                      int64_t ldv, int* r);
+/* Asynchronous `update_sol!` (primitives.jl:82-90: `deepcopy(integrator.u)` after every step) / save-at: snapshot the
+ * current factors into HOST buffers (pinned for a truly asynchronous copy) without stalling the step stream — staged on the
+ * device, moved by the copy stream while later steps run.  *r receives the rank immediately; the buffers are valid after
+ * dlra_save_wait (or dlra_sync + dlra_save_wait).  At most two snapshots are in flight; a third waits on the device. */
+int dlra_save_factors_async(dlra_handle h, double* U_host, int64_t ldu, double* S_host, int64_t lds, double* V_host,
+                            int64_t ldv, int* r);
+int dlra_save_wait(dlra_handle h);
 int dlra_get_rank(dlra_handle h, int* r);
 /* truncated_svd(A, r) / truncated_svd(A; tol) (LowRankArithmetic; call sites test/data_driven_approximation.jl:18,
  * examples/generic_matrix.jl:29) for matrices that only exist on the device: randomized subspace
@@ -151,6 +160,10 @@ int dlra_rhs_set(dlra_handle h, const dlra_operator* A, const dlra_operator* B, 
 int dlra_rhs_add_term(dlra_handle h, const dlra_operator* A, const dlra_operator* B);
 /* K_alg / S_alg / L_alg and their tolerances (Tsit5 defaults abstol=1e-6, reltol=1e-3) */
 int dlra_set_substepper(dlra_handle h, int flow, int ode, int nsub, double abstol, double reltol);
+/* `maxiters` of the adaptive sub-stepper of one flow (OrdinaryDiffEq default 100000, the value the reference's
+ * `init(ODEProblem, Tsit5(); save_everystep=false)` integrators run with, unconventional.jl:59): accepted + rejected
+ * sub-steps allowed inside one outer step before the step fails with DLRA_EMAXITERS. */
+int dlra_set_substepper_maxiters(dlra_handle h, int flow, int64_t maxiters);
 
 /* ---- steps: one call == one reference step!(integrator, alg, dt) minus the t/iter bookkeeping -- */
 /* primal_LT_step! / dual_LT_step! / Strang (projector_splitting.jl:117-211).  For data problems
@@ -182,6 +195,16 @@ int dlra_sync(dlra_handle h);
  * producing stream on the host, or call this with that stream (a cudaStream_t; NULL = the legacy default stream) — the
  * engine stream then waits for everything enqueued there so far (event record + cudaStreamWaitEvent, no host blocking). */
 int dlra_wait_stream(dlra_handle h, void* producer_stream);
+/* The engine's compute stream (a cudaStream_t), for the opposite direction: a caller whose allocator recycles device memory
+ * by stream (Julia's CUDA.jl pool, PyTorch's caching allocator: `tensor.record_stream`) registers borrowed snapshots with this
+ * stream so that a freed snapshot is not handed out again while a queued step still reads it (data is borrowed read-only and
+ * the steps are asynchronous; the reference's `y` is never freed under the integrator, primitives.jl:23-30). */
+int dlra_get_stream(dlra_handle h, void** stream);
+/* Steps are asynchronous: *steps_enqueued counts the dlra_step_* calls made so far, *steps_completed those whose work has
+ * finished on the device (polled without blocking).  wait_for > *steps_completed blocks until that many steps are done
+ * (pass -1 never to block).  A borrowed snapshot that served step k as "current" is last read by step k+1: callers that
+ * recycle snapshot memory release it once steps_completed >= k+1. */
+int dlra_progress(dlra_handle h, int64_t* steps_enqueued, int64_t* steps_completed, int64_t wait_for);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* ‖U·S·Vᵀ − Yref‖_F / ‖Yref‖_F without materialising n x m on the host (Yref: n_local x m device);

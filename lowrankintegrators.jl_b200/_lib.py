@@ -11,7 +11,7 @@ c_int_p = C.POINTER(C.c_int)
 c_i64_p = C.POINTER(C.c_int64)
 handle_t = C.c_void_p
 
-OK, EINVAL, ECUDA, ENCCL, ESTATE, ENOMEM, EUNSUPPORTED = range(7)
+OK, EINVAL, ECUDA, ENCCL, ESTATE, ENOMEM, EUNSUPPORTED, EMAXITERS = range(8)
 RANK_ADAPTIVE, FORCE_GENERIC, AUG_BASIS_FIRST = 1, 2, 4
 KSL_PRIMAL, KSL_DUAL, KSL_STRANG = 0, 1, 2
 DATA_SNAPSHOT, DATA_DELTA = 0, 1
@@ -42,6 +42,8 @@ SIGNATURES = {
     "dlra_get_factors_host": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_int_p]),
     "dlra_get_factors": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_int_p]),
     "dlra_get_rank": (C.c_int, [handle_t, c_int_p]),
+    "dlra_save_factors_async": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, c_int_p]),
+    "dlra_save_wait": (C.c_int, [handle_t]),
     "dlra_truncated_svd": (C.c_int, [handle_t, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint64]),
     "dlra_factor_ptrs": (C.c_int, [handle_t, C.POINTER(C.c_void_p), c_i64_p, C.POINTER(C.c_void_p), c_i64_p,
                                    C.POINTER(C.c_void_p), c_i64_p, c_int_p]),
@@ -53,6 +55,7 @@ SIGNATURES = {
                                C.c_int, C.POINTER(Operator), C.POINTER(Operator), C.c_double]),
     "dlra_rhs_add_term": (C.c_int, [handle_t, C.POINTER(Operator), C.POINTER(Operator)]),
     "dlra_set_substepper": (C.c_int, [handle_t, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]),
+    "dlra_set_substepper_maxiters": (C.c_int, [handle_t, C.c_int, C.c_int64]),
     "dlra_step_ksl": (C.c_int, [handle_t, C.c_int, C.c_double, C.c_double]),
     "dlra_step_bug": (C.c_int, [handle_t, C.c_double, C.c_double]),
     "dlra_step_rabug": (C.c_int, [handle_t, C.c_double, C.c_double, C.c_double, C.c_int64, c_int_p, c_int_p]),
@@ -62,6 +65,8 @@ SIGNATURES = {
                                         c_double_p]),
     "dlra_sync": (C.c_int, [handle_t]),
     "dlra_wait_stream": (C.c_int, [handle_t, C.c_void_p]),
+    "dlra_get_stream": (C.c_int, [handle_t, C.POINTER(C.c_void_p)]),
+    "dlra_progress": (C.c_int, [handle_t, c_i64_p, c_i64_p, C.c_int64]),
     "dlra_reconstruct_error": (C.c_int, [handle_t, C.c_void_p, C.c_int64, c_double_p]),
     "dlra_reconstruct": (C.c_int, [handle_t, C.c_void_p, C.c_int64]),
     "dlra_stats": (C.c_int, [handle_t, c_i64_p, c_i64_p, c_double_p, c_double_p, C.c_int]),

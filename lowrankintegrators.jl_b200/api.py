@@ -168,6 +168,21 @@ class DLRIntegrator:
         return {"U": U, "S": S, "V": V, "t": self.t, "iter": self.iter}
 
 
+class _PendingSave:
+    def __init__(self, fac, two_factor):
+        self.fac, self.two_factor = fac, two_factor
+
+    def resolve(self):
+        U, S, V = self.fac
+        return TwoFactorRepresentation(U, V) if self.two_factor else SVDLikeRepresentation(U, S, V)
+
+
+def finish_saves(integ):
+    """Wait for the asynchronous factor snapshots and turn the pending entries of integ.sol.Y into representations."""
+    integ.cache.save_wait()
+    integ.sol.Y[:] = [y.resolve() if isinstance(y, _PendingSave) else y for y in integ.sol.Y]
+
+
 def init_sol(dt, t0, tf, u0):  # primitives.jl:92-104
     if isinstance(dt, (int, np.integer)) and not isinstance(dt, bool):
         steps = list(range(t0, tf + 1, dt))
@@ -177,7 +192,12 @@ def init_sol(dt, t0, tf, u0):  # primitives.jl:92-104
 
 
 def update_sol(integ):  # primitives.jl:82-90
-    u = integ.u if integ.save_everystep else None
+    if integ.save_everystep and getattr(integ, "async_save", False):
+        # the deep copy of u goes through pinned host memory on the copy stream while the next steps run; entries are
+        # (U, S, V) views until solve() / finish_saves() has waited for the copies and wrapped them
+        u = _PendingSave(integ.cache.save_factors_async(), integ.two_factor)
+    else:
+        u = integ.u if integ.save_everystep else None
     if integ.iter <= len(integ.sol.Y) - 1:
         integ.sol.Y[integ.iter] = u
         integ.sol.t[integ.iter] = integ.t
@@ -210,6 +230,7 @@ class SubStepper:
     nsub: int = 1
     abstol: float = 1e-6
     reltol: float = 1e-3
+    maxiters: int = 100000   # OrdinaryDiffEq default; the step raises DLRAError(EMAXITERS) beyond it
 
 
 _ODE = {"euler": L.ODE_EULER, "rk4": L.ODE_RK4, "tsit5_fixed": L.ODE_TSIT5_FIXED, "tsit5": L.ODE_TSIT5}
@@ -269,7 +290,7 @@ def _has_snapshot(y, tspan, t, ahead):
 
 
 def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_generic=False, lookahead=True, resume=None,
-         aug_basis_first=False) -> DLRIntegrator:
+         aug_basis_first=False, async_save=False) -> DLRIntegrator:
     """init(prob, alg, dt): projector_splitting.jl:107-115, unconventional.jl:109-119,
     rank_adaptive_unconventional.jl:94-104, greedy_integrator.jl:49-59.  `comm` = "torch" (use the initialised torch.distributed group to distribute
     a fresh ncclUniqueId) or (nranks, rank, unique_id) row-shards the problem: every rank passes ITS row block of u0.U
@@ -310,18 +331,19 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     elif isinstance(prob, MatrixHybridProblem):  # greedy_integrator.jl:41-47: ZIntegrator = init(ODEProblem(f, Z, tspan, U), Z_alg)
         prob.f.install(eng)
         sub = alg.Z_alg or SubStepper()
-        eng.set_substepper(L.FLOW_L, _ODE[sub.kind], sub.nsub, sub.abstol, sub.reltol)
+        eng.set_substepper(L.FLOW_L, _ODE[sub.kind], sub.nsub, sub.abstol, sub.reltol, sub.maxiters)
     else:
         if isinstance(alg, GreedyIntegrator):
             raise TypeError("MethodError: GreedyIntegrator is defined for data problems")
         prob.f.install(eng)
         for flow, sub in ((L.FLOW_K, alg.K_alg), (L.FLOW_S, alg.S_alg), (L.FLOW_L, alg.L_alg)):
             sub = sub or SubStepper()
-            eng.set_substepper(flow, _ODE[sub.kind], sub.nsub, sub.abstol, sub.reltol)
+            eng.set_substepper(flow, _ODE[sub.kind], sub.nsub, sub.abstol, sub.reltol, sub.maxiters)
     sol = init_sol(dt, t0, tf, u0)
     sol.Y[0] = u0.copy() if hasattr(u0, "copy") else u0
     integ = DLRIntegrator(eng, t0, dt, sol, alg, type(prob), prob, save_everystep)
     integ.lookahead = bool(lookahead)
+    integ.async_save = bool(async_save)   # update_sol! through dlra_save_factors_async (pinned host buffers, copy stream)
     if resume is not None:
         integ.iter = 0   # sol restarts at the checkpoint; resume["iter"] tells the caller where that was
     return integ
@@ -402,4 +424,6 @@ def solve(prob, alg, dt=None, **kw) -> DLRSolution:
     if not integ.save_everystep:
         integ.sol.Y[-1] = integ.u
     integ.cache.sync()
+    if integ.async_save:
+        finish_saves(integ)
     return integ.sol

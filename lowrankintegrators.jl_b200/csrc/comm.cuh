@@ -81,6 +81,36 @@ __global__ void __launch_bounds__(256) p2p_gather_kernel(P2PView v, double* __re
     }
 }
 
+// Small-message all-reduce in ONE single-CTA launch: up to four little matrices (leading dimension ld) are packed into the
+// exchange buffer, the rank's flag is raised in every peer, the peers' packs are summed in rank order and unpacked in place.
+// Replaces (copy_mat x2, post, sum, copy_mat x2) of the M / core-increment reduction of a BUG step.
+struct SmallMats {
+    double* p[4]; int rows[4], cols[4]; int64_t ld[4]; int n;
+};
+__global__ void __launch_bounds__(256) p2p_small_allreduce_kernel(P2PView v, SmallMats sm) {
+    int64_t off = 0;
+    for (int q = 0; q < sm.n; ++q) {
+        const int cnt = sm.rows[q] * sm.cols[q];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x)
+            v.data_local[off + e] = sm.p[q][(e % sm.rows[q]) + (int64_t)(e / sm.rows[q]) * sm.ld[q]];
+        off += cnt;
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x < v.nranks) st_release_sys(v.flags_peer[threadIdx.x] + (size_t)v.rank * P2P_FLAG_STRIDE, v.seq);
+    p2p_wait_all(v);
+    off = 0;
+    for (int q = 0; q < sm.n; ++q) {
+        const int cnt = sm.rows[q] * sm.cols[q];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) {
+            double s = 0.0;
+            for (int g = 0; g < v.nranks; ++g) s += ld_relaxed_sys(v.data_peer[g] + off + e);
+            sm.p[q][(e % sm.rows[q]) + (int64_t)(e / sm.rows[q]) * sm.ld[q]] = s;
+        }
+        off += cnt;
+    }
+}
+
 struct Comm {
     struct UniqueId { char internal[128]; };
     int nranks = 1, rank = 0;
@@ -98,8 +128,11 @@ struct Comm {
     char* xbuf = nullptr;             // local exchange region: [flags 8 x 128 B][data parity 0][data parity 1]
     size_t xdata_bytes = 0;           // bytes of ONE parity buffer
     char* xpeer[P2P_MAX_RANKS] = {};
-    unsigned long long seq = 0;
-    unsigned int* ticket = nullptr;   // device counter for the post kernel
+    // two independent channels (own flags, parity buffers, sequence numbers, ticket): channel 0 serves the main stream, channel 1
+    // the auxiliary stream (the L all-reduce runs there beside the K-side TSQR, whose R all-gather uses channel 0)
+    static constexpr int NCHAN = 2;
+    unsigned long long seq[NCHAN] = {0, 0};
+    unsigned int* ticket = nullptr;   // device counters for the post kernels, one per channel
 
     static constexpr size_t FLAG_BYTES = (size_t)P2P_MAX_RANKS * P2P_FLAG_STRIDE * sizeof(unsigned long long);
 
@@ -140,11 +173,12 @@ struct Comm {
     void p2p_alloc(size_t data_bytes) {
         if (xbuf) return;
         xdata_bytes = (data_bytes + 255) / 256 * 256;
-        DLRA_CUDA(cudaMalloc(&xbuf, FLAG_BYTES + 2 * xdata_bytes));
-        DLRA_CUDA(cudaMemset(xbuf, 0, FLAG_BYTES + 2 * xdata_bytes));
-        DLRA_CUDA(cudaMalloc(&ticket, sizeof(unsigned int)));
-        DLRA_CUDA(cudaMemset(ticket, 0, sizeof(unsigned int)));
+        DLRA_CUDA(cudaMalloc(&xbuf, NCHAN * chan_bytes()));
+        DLRA_CUDA(cudaMemset(xbuf, 0, NCHAN * chan_bytes()));
+        DLRA_CUDA(cudaMalloc(&ticket, NCHAN * sizeof(unsigned int)));
+        DLRA_CUDA(cudaMemset(ticket, 0, NCHAN * sizeof(unsigned int)));
     }
+    size_t chan_bytes() const { return FLAG_BYTES + 2 * xdata_bytes; }
     void p2p_export(void* handle64) {
         cudaIpcMemHandle_t hd;
         DLRA_CUDA(cudaIpcGetMemHandle(&hd, xbuf));
@@ -175,18 +209,51 @@ struct Comm {
         if (ticket) cudaFree(ticket);
         xbuf = nullptr; ticket = nullptr; p2p = false;
     }
-    P2PView next_view() {
-        ++seq;
-        const size_t par = (size_t)(seq & 1);
+    // Buffer reuse is safe by stream order: a rank posts message s+2 of a channel (same parity buffer as s) only after its own
+    // wait for message s+1, i.e. after every peer has posted s+1, which every peer does after it finished reading message s.
+    P2PView next_view(int chan = 0) {
+        const unsigned long long sq = ++seq[chan];
+        const size_t par = (size_t)(sq & 1);
+        const size_t cb = (size_t)chan * chan_bytes();
         P2PView v;
-        v.nranks = nranks; v.rank = rank; v.seq = seq;
-        v.flags_local = (unsigned long long*)xbuf;
+        v.nranks = nranks; v.rank = rank; v.seq = sq;
+        v.flags_local = (unsigned long long*)(xbuf + cb);
         for (int g = 0; g < P2P_MAX_RANKS; ++g) {
-            v.flags_peer[g] = (unsigned long long*)(xpeer[g] ? xpeer[g] : xbuf);
-            v.data_peer[g] = (const double*)((xpeer[g] ? xpeer[g] : xbuf) + FLAG_BYTES + par * xdata_bytes);
+            char* base = (xpeer[g] ? xpeer[g] : xbuf) + cb;
+            v.flags_peer[g] = (unsigned long long*)base;
+            v.data_peer[g] = (const double*)(base + FLAG_BYTES + par * xdata_bytes);
         }
-        v.data_local = (double*)(xbuf + FLAG_BYTES + par * xdata_bytes);
+        v.data_local = (double*)(xbuf + cb + FLAG_BYTES + par * xdata_bytes);
         return v;
+    }
+    unsigned int* ticket_of(int chan) { return ticket + chan; }
+
+    // in-place sum over ranks of up to four small matrices: one launch on the P2P transport
+    void allreduce_small_mats(SmallMats sm, double* staging, Ctx& cx) {
+        if (nranks <= 1 || sm.n <= 0) return;
+        int64_t total = 0;
+        for (int q = 0; q < sm.n; ++q) total += (int64_t)sm.rows[q] * sm.cols[q];
+        if (p2p && (size_t)total * 8 <= xdata_bytes && total <= 65536) {
+            P2PView v = next_view(0);
+            p2p_small_allreduce_kernel<<<1, 256, 0, cx.stream>>>(v, sm);
+            cx.launches++;
+            DLRA_CUDA(cudaGetLastError());
+            return;
+        }
+        // library transport: pack densely, one all-reduce, unpack
+        int64_t off = 0;
+        for (int q = 0; q < sm.n; ++q) {
+            DLRA_CUDA(cudaMemcpy2DAsync(staging + off, (size_t)sm.rows[q] * 8, sm.p[q], (size_t)sm.ld[q] * 8, (size_t)sm.rows[q] * 8, sm.cols[q],
+                                        cudaMemcpyDeviceToDevice, cx.stream));
+            off += (int64_t)sm.rows[q] * sm.cols[q];
+        }
+        allreduce_sum(staging, total, cx);
+        off = 0;
+        for (int q = 0; q < sm.n; ++q) {
+            DLRA_CUDA(cudaMemcpy2DAsync(sm.p[q], (size_t)sm.ld[q] * 8, staging + off, (size_t)sm.rows[q] * 8, (size_t)sm.rows[q] * 8, sm.cols[q],
+                                        cudaMemcpyDeviceToDevice, cx.stream));
+            off += (int64_t)sm.rows[q] * sm.cols[q];
+        }
     }
 
     // in-place sum over ranks
@@ -194,7 +261,7 @@ struct Comm {
         if (nranks <= 1 || count <= 0) return;
         if (p2p) {
             DLRA_REQUIRE((size_t)count * 8 <= xdata_bytes, "P2P exchange region too small for this message");
-            P2PView v = next_view();
+            P2PView v = next_view(0);
             const int blocks = (int)std::min<int64_t>(cdiv(count, 1024), cx.num_sms);
             p2p_post_kernel<<<blocks, 256, 0, cx.stream>>>(v, buf, count, ticket);
             p2p_sum_kernel<<<blocks, 256, 0, cx.stream>>>(v, buf, count);
@@ -211,7 +278,7 @@ struct Comm {
         }
         if (p2p) {
             DLRA_REQUIRE((size_t)count_per_rank * 8 <= xdata_bytes, "P2P exchange region too small for this message");
-            P2PView v = next_view();
+            P2PView v = next_view(0);
             const int blocks = (int)std::min<int64_t>(cdiv(count_per_rank * nranks, 1024), cx.num_sms);
             p2p_post_kernel<<<std::max(1, (int)std::min<int64_t>(cdiv(count_per_rank, 1024), cx.num_sms)), 256, 0, cx.stream>>>(v, send, count_per_rank, ticket);
             p2p_gather_kernel<<<blocks, 256, 0, cx.stream>>>(v, recv, count_per_rank);

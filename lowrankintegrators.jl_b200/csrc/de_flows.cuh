@@ -413,9 +413,11 @@ inline void ode_advance(dlra_engine* e, SubStepperCfg& st, FlowRhs& f, int64_t N
     }
     double h = st.dt_next;
     const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 0.9, qmin = 0.2, qmax = 10.0;
-    int guard = 0;
+    int64_t guard = 0;
     while ((tend - t) > 1e-14 * std::max(1.0, fabs(tend))) {
-        DLRA_REQUIRE(++guard < 100000, "adaptive Tsit5 did not reach the end of the step");
+        if (++guard > st.maxiters)
+            throw CudaError(DLRA_EMAXITERS, "adaptive Tsit5 reached maxiters before the end of the step (stiff or unstable projected flow; "
+                                            "factors and controller state are those before the step)");
         h = std::min(h, tend - t);
         tsit5_stages(e, f, N, X, t, h, ks, utmp, unew);
         st.nfev += 6;

@@ -83,6 +83,7 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
             DLRA_CUDA(cudaEventCreateWithFlags(&e->own_ready[i], cudaEventDisableTiming));
         }
         e->sub[0] = SubStepperCfg(); e->sub[1] = SubStepperCfg(); e->sub[2] = SubStepperCfg();
+        e->phase_timing = getenv("DLRA_PHASES") != nullptr;
         DLRA_CUDA(cudaStreamSynchronize(e->cx.stream));
     } catch (const CudaError& ex) {
         g_create_error = ex.what();
@@ -112,10 +113,17 @@ extern "C" int dlra_destroy(dlra_handle h) {
         if (h->own_free[i]) cudaEventDestroy(h->own_free[i]);
         if (h->own_ready[i]) cudaEventDestroy(h->own_ready[i]);
     }
-    h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release();
+    h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release(); h->isvd.release();
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto& pm : h->phase_marks) cudaEventDestroy(pm.second);
+    for (int i = 0; i < dlra_engine::NPROG; ++i) if (h->prog_ev[i]) cudaEventDestroy(h->prog_ev[i]);
     for (int i = 0; i < 8; ++i) if (h->user_events[i]) cudaEventDestroy(h->user_events[i]);
     de_release(h);
+    for (int i = 0; i < 2; ++i) {
+        h->save_stage[i].release();
+        if (h->save_staged[i]) cudaEventDestroy(h->save_staged[i]);
+        if (h->save_landed[i]) cudaEventDestroy(h->save_landed[i]);
+    }
     h->gws2.release(); h->tws2.release(); h->wtmp2.release(); h->zcarry.k.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -141,6 +149,21 @@ extern "C" int dlra_wait_stream(dlra_handle h, void* producer_stream) {
     DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->ev_ext, 0));
     DLRA_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_ext, 0));
     DLRA_API_END(h)
+}
+
+static void progress_poll(dlra_handle h, int64_t wait_for);
+extern "C" int dlra_progress(dlra_handle h, int64_t* steps_enqueued, int64_t* steps_completed, int64_t wait_for) {
+    DLRA_API_BEGIN(h)
+    progress_poll(h, std::min(wait_for, h->steps_enqueued));
+    if (steps_enqueued) *steps_enqueued = h->steps_enqueued;
+    if (steps_completed) *steps_completed = h->steps_completed;
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_get_stream(dlra_handle h, void** stream) {
+    if (!h || !stream) return DLRA_EINVAL;
+    *stream = (void*)h->cx.stream;
+    return DLRA_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -229,6 +252,44 @@ extern "C" int dlra_get_factors_host(dlra_handle h, double* U, int64_t ldu, doub
 extern "C" int dlra_get_factors(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V, int64_t ldv, int* r) {
     DLRA_API_BEGIN(h)
     get_factors_impl(h, U, ldu, S, lds, V, ldv, r, cudaMemcpyDeviceToDevice);
+    DLRA_API_END(h)
+}
+// update_sol! without stalling the step stream (primitives.jl:82-90 deep-copies u after every step): the factors are copied
+// device-to-device into one of two staging slots ON the compute stream (a few µs), and the copy stream moves the slot to the
+// caller's (pinned) host buffers while the next steps run.  The compute stream only waits if both slots are still in flight.
+extern "C" int dlra_save_factors_async(dlra_handle h, double* U, int64_t ldu, double* S, int64_t lds, double* V, int64_t ldv, int* r) {
+    DLRA_API_BEGIN(h)
+    const int rr = h->r;
+    DLRA_REQUIRE(U && S && V && ldu >= h->n && lds >= rr && ldv >= h->m, "bad factor pointers / leading dimensions");
+    const int slot = h->save_next;
+    h->save_next ^= 1;
+    if (!h->save_staged[slot]) {
+        DLRA_CUDA(cudaEventCreateWithFlags(&h->save_staged[slot], cudaEventDisableTiming));
+        DLRA_CUDA(cudaEventCreateWithFlags(&h->save_landed[slot], cudaEventDisableTiming));
+    } else {
+        DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->save_landed[slot], 0));   // the previous D2H out of this slot is done
+    }
+    const int64_t W = h->W;
+    h->save_stage[slot].ensure((h->n + h->m + W) * W, h->cx.stream);
+    double* su = h->save_stage[slot].p;
+    double* sv = su + h->n * W;
+    double* ss = sv + h->m * W;
+    cudaStream_t cs = h->cx.stream, ds = h->copy_stream;
+    DLRA_CUDA(cudaMemcpyAsync(su, h->U, (size_t)h->n * rr * 8, cudaMemcpyDeviceToDevice, cs));
+    DLRA_CUDA(cudaMemcpyAsync(sv, h->V, (size_t)h->m * rr * 8, cudaMemcpyDeviceToDevice, cs));
+    DLRA_CUDA(cudaMemcpy2DAsync(ss, (size_t)rr * 8, h->S, (size_t)W * 8, (size_t)rr * 8, rr, cudaMemcpyDeviceToDevice, cs));
+    DLRA_CUDA(cudaEventRecord(h->save_staged[slot], cs));
+    DLRA_CUDA(cudaStreamWaitEvent(ds, h->save_staged[slot], 0));
+    DLRA_CUDA(cudaMemcpy2DAsync(U, ldu * 8, su, h->n * 8, h->n * 8, rr, cudaMemcpyDeviceToHost, ds));
+    DLRA_CUDA(cudaMemcpy2DAsync(V, ldv * 8, sv, h->m * 8, h->m * 8, rr, cudaMemcpyDeviceToHost, ds));
+    DLRA_CUDA(cudaMemcpy2DAsync(S, lds * 8, ss, (size_t)rr * 8, (size_t)rr * 8, rr, cudaMemcpyDeviceToHost, ds));
+    DLRA_CUDA(cudaEventRecord(h->save_landed[slot], ds));
+    if (r) *r = rr;
+    DLRA_API_END(h)
+}
+extern "C" int dlra_save_wait(dlra_handle h) {
+    DLRA_API_BEGIN(h)
+    for (int i = 0; i < 2; ++i) if (h->save_landed[i]) DLRA_CUDA(cudaEventSynchronize(h->save_landed[i]));
     DLRA_API_END(h)
 }
 extern "C" int dlra_get_rank(dlra_handle h, int* r) {
@@ -394,17 +455,19 @@ static void qr_mside(dlra_handle h, Side sd, double* A, int C, double* R, int or
     ensure_qr_ws(sd, h->m, C);
     thin_qr(*sd.cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, sd.tws->p, sd.gws->p, sd.wtmp->p, ortho_cols);
 }
+// p x q small matrix with ld W, summed over the row shards in place
+static void allreduce_small(dlra_handle h, double* C, int p, int q) {
+    if (h->comm.nranks <= 1) return;
+    SmallMats sm;
+    sm.n = 1;
+    sm.p[0] = C; sm.rows[0] = p; sm.cols[0] = q; sm.ld[0] = h->W;
+    h->comm.allreduce_small_mats(sm, h->stg, h->cx);
+}
 // C (p x q, ld W) = A' * B over the sharded n dimension (+ all-reduce)
 static void gram_nside(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
     h->gws.ensure(gemm_tn_ws(h->cx, h->n, p, q), h->cx.stream);
-    if (h->comm.nranks > 1) {
-        // reduce into a dense p x q staging block so one collective suffices
-        gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, h->T2, p, 1.0, 0.0, h->gws.p);
-        h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx);
-        copy_mat(h->cx, p, q, h->T2, p, false, C, h->W);
-    } else {
-        gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, C, h->W, 1.0, 0.0, h->gws.p);
-    }
+    gemm_tn(h->cx, h->n, p, q, A, h->n, nullptr, 0, B, h->n, C, h->W, 1.0, 0.0, h->gws.p);
+    allreduce_small(h, C, p, q);
 }
 // local (this rank's rows) part of A'*B: the cross-rank sum is deferred and merged with a later collective
 static void gram_nside_local(dlra_handle h, int p, int q, const double* A, const double* B, double* C) {
@@ -414,23 +477,15 @@ static void gram_nside_local(dlra_handle h, int p, int q, const double* A, const
 // one all-reduce for two small matrices (ld W): halves the number of cross-GPU synchronisation points per step
 static void allreduce_pair(dlra_handle h, double* A, int pa, int qa, double* B, int pb, int qb) {
     if (h->comm.nranks <= 1) return;
-    double* st = h->stg;   // 8*W*W doubles
-    copy_mat(h->cx, pa, qa, A, h->W, false, st, pa);
-    copy_mat(h->cx, pb, qb, B, h->W, false, st + (int64_t)pa * qa, pb);
-    h->comm.allreduce_sum(st, (int64_t)pa * qa + (int64_t)pb * qb, h->cx);
-    copy_mat(h->cx, pa, qa, st, pa, false, A, h->W);
-    copy_mat(h->cx, pb, qb, st + (int64_t)pa * qa, pb, false, B, h->W);
+    SmallMats sm;
+    sm.n = 2;
+    sm.p[0] = A; sm.rows[0] = pa; sm.cols[0] = qa; sm.ld[0] = h->W;
+    sm.p[1] = B; sm.rows[1] = pb; sm.cols[1] = qb; sm.ld[1] = h->W;
+    h->comm.allreduce_small_mats(sm, h->stg /* 8*W*W doubles */, h->cx);   // P2P transport: one single-CTA launch
 }
 static void gram_mside(dlra_handle h, Side sd, int p, int q, const double* A, const double* B, double* C) {
     sd.gws->ensure(gemm_tn_ws(*sd.cx, h->m, p, q), sd.cx->stream);
     gemm_tn(*sd.cx, h->m, p, q, A, h->m, nullptr, 0, B, h->m, C, h->W, 1.0, 0.0, sd.gws->p);
-}
-// p x q small matrix with ld W: stage densely, reduce, copy back
-static void allreduce_small(dlra_handle h, double* C, int p, int q) {
-    if (h->comm.nranks <= 1) return;
-    copy_mat(h->cx, p, q, C, h->W, false, h->T2, p);
-    h->comm.allreduce_sum(h->T2, (int64_t)p * q, h->cx);
-    copy_mat(h->cx, p, q, h->T2, p, false, C, h->W);
 }
 
 // K-flow / L-flow / S-flow of one outer step: data problems contract the increment, DE problems integrate
@@ -453,7 +508,9 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     // K = U0*S0 (+ ΔA*V0);  L = V0*S0' (+ ΔA'*U0)   — one fused read of ΔA
     const bool pre = sc.is_data && h->kl_ready && h->kl_rank == r;   // formed by the previous step's pipelined pass
     h->kl_ready = false;
-    const bool lfin_aux = pre && h->comm.nranks <= 1;   // single GPU: the whole L-side chain runs beside the K-side chain
+    phase_mark(h, "step");
+    // the whole L-side chain (incl. the cross-rank sum of L on exchange channel 1) runs beside the K-side chain
+    const bool lfin_aux = pre && (h->comm.nranks <= 1 || h->comm.p2p) && !getenv("DLRA_LFIN_MAIN");
     if (pre) {
         // K = ΔA*V0 (already in UB) + U0*S0: the update is folded into the TSQR panel load below
         if (!lfin_aux)
@@ -469,14 +526,18 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
         de_K_flow(h, K, r, h->V, sc.t, sc.dt);
         de_L_flow(h, L, r, h->U, sc.t, sc.dt);
     }
+    phase_mark(h, "KL_or_Lsum");
     fork_aux(h);                                          // m-side chain on the auxiliary stream ...
     if (lfin_aux) l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, 16, 1, h->V, m, h->S, W, r, L, m, &h->ax);
     qr_mside(h, aux_side(h), L, r, nullptr);              // V1 = qr(L).Q
     gram_mside(h, aux_side(h), r, r, L, h->V, h->N);      // N = V1'*V0
     if (pre) qr_nside_plus(h, K, r, h->U, h->S, r);       // ... overlaps U1 = qr(ΔA*V0 + U0*S0).Q
     else qr_nside(h, K, r, nullptr);                      //              U1 = qr(K).Q
+    phase_mark(h, "qr_K");
     gram_nside_local(h, r, r, K, h->U, h->M);             // M = U1'*U0 (local rows; summed over ranks below)
+    phase_mark(h, "gram_M");
     join_aux(h);
+    phase_mark(h, "join_Lside");
     if (sc.is_data) {
         const bool pipe = !(h->flags & DLRA_FORCE_GENERIC) && h->have_nxt && h->nxt_kind == DLRA_DATA_SNAPSHOT && sc.d.Aprev != nullptr &&
                           r <= 16 && tma_pass_supported(n, m, sc.d) && tma_ok(h->nxt, h->ldnxt);
@@ -497,8 +558,11 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
         } else {
             pass_S(h, sc.d, r, r, K, n, L, m, h->Rm, W);        // Rm = U1'*ΔA*V1 (local rows)
         }
+        phase_mark(h, "pass_S(+KL_next)+gram");
         allreduce_pair(h, h->M, r, r, h->Rm, r, r);             // M and the core increment share one collective
+        phase_mark(h, "allreduce_M_S");
         core_update(cx, r, r, r, h->M, h->S, h->N, h->Rm, h->S, (int)W, h->T1);   // S1 = M*S0*N' + U1'*ΔA*V1 (one launch)
+        phase_mark(h, "core_update");
         std::swap(h->U, h->UB);
         std::swap(h->V, h->VB);
         return;
@@ -700,6 +764,46 @@ static void greedy_two_factor_step(dlra_handle h, const Delta& x, int mode, bool
 // ---------------------------------------------------------------------------------------------------
 // step entry points
 // ---------------------------------------------------------------------------------------------------
+// A step that throws (sub-stepper maxiters, non-finite state, CUDA error) must leave the handle usable: U, S, V are only
+// replaced at the very end of a step (pointer swap / final copy), so they still hold the factors before the step; this guard
+// puts the adaptive controllers back, drops the precomputed K/L pass and re-joins the auxiliary stream.
+static void progress_poll(dlra_handle h, int64_t wait_for) {
+    while (h->steps_completed < h->steps_enqueued) {
+        cudaEvent_t ev = h->prog_ev[(h->steps_completed + 1) % dlra_engine::NPROG];
+        if (h->steps_completed < wait_for) DLRA_CUDA(cudaEventSynchronize(ev));
+        else {
+            cudaError_t q = cudaEventQuery(ev);
+            if (q == cudaErrorNotReady) break;
+            DLRA_CUDA(q);
+        }
+        h->steps_completed++;
+    }
+}
+// every step entry point ends with this: event k marks the completion of step k on the compute stream
+static void progress_mark(dlra_handle h) {
+    if (h->steps_enqueued - h->steps_completed >= dlra_engine::NPROG - 1) progress_poll(h, h->steps_completed + 1);   // ring full
+    const int64_t k = ++h->steps_enqueued;
+    cudaEvent_t& ev = h->prog_ev[k % dlra_engine::NPROG];
+    if (!ev) DLRA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    DLRA_CUDA(cudaEventRecord(ev, h->cx.stream));
+}
+
+struct StepGuard {
+    dlra_handle h;
+    SubStepperCfg saved[3];
+    bool ok = false;
+    explicit StepGuard(dlra_handle hh) : h(hh) { for (int i = 0; i < 3; ++i) saved[i] = h->sub[i]; }
+    void commit() { ok = true; progress_mark(h); }
+    ~StepGuard() {
+        if (ok) return;
+        for (int i = 0; i < 3; ++i) h->sub[i] = saved[i];
+        h->kl_ready = false;
+        h->zcarry.valid = false;
+        cudaStreamSynchronize(h->ax.stream);
+        cudaStreamSynchronize(h->cx.stream);
+    }
+};
+
 static StepCtx make_ctx(dlra_handle h, double t, double dt) {
     StepCtx sc;
     sc.t = t; sc.dt = dt;
@@ -710,6 +814,7 @@ static StepCtx make_ctx(dlra_handle h, double t, double dt) {
 
 extern "C" int dlra_step_ksl(dlra_handle h, int order, double t, double dt) {
     DLRA_API_BEGIN(h)
+    StepGuard guard(h);
     DLRA_REQUIRE(order == DLRA_KSL_PRIMAL || order == DLRA_KSL_DUAL || order == DLRA_KSL_STRANG, "bad KSL order");
     if (order == DLRA_KSL_STRANG) {
         DLRA_REQUIRE(h->rhs.set, "Strang on a data problem needs two increments: push, PRIMAL(dt/2), push, DUAL(dt/2)");
@@ -722,23 +827,28 @@ extern "C" int dlra_step_ksl(dlra_handle h, int order, double t, double dt) {
         if (order == DLRA_KSL_PRIMAL) ksl_primal_step(h, sc); else ksl_dual_step(h, sc);
         if (sc.is_data) end_data_step(h);
     }
+    guard.commit();
     DLRA_API_END(h)
 }
 
 extern "C" int dlra_step_bug(dlra_handle h, double t, double dt) {
     DLRA_API_BEGIN(h)
+    StepGuard guard(h);
     StepCtx sc = make_ctx(h, t, dt);
     bug_step(h, sc);
     if (sc.is_data) end_data_step(h);
+    guard.commit();
     DLRA_API_END(h)
 }
 
 extern "C" int dlra_step_rabug(dlra_handle h, double t, double dt, double tol, int64_t rmax, int* r_new, int* rank_changed) {
     DLRA_API_BEGIN(h)
+    StepGuard guard(h);
     DLRA_REQUIRE(tol >= 0.0 && rmax >= 1, "bad tolerance / rank cap");
     StepCtx sc = make_ctx(h, t, dt);
     rabug_step(h, sc, tol, rmax, r_new, rank_changed);
     if (sc.is_data) end_data_step(h);
+    guard.commit();
     DLRA_API_END(h)
 }
 
@@ -749,6 +859,7 @@ extern "C" int dlra_step_greedy(dlra_handle h, double t, double dt) {
     Delta x = begin_data_step(h, true);
     greedy_step(h, x);
     end_data_step(h);
+    progress_mark(h);
     DLRA_API_END(h)
 }
 
@@ -757,9 +868,11 @@ extern "C" int dlra_step_greedy_two_factor(dlra_handle h, int mode, int carry_fs
     DLRA_REQUIRE(mode == DLRA_GREEDY_DATA || mode == DLRA_GREEDY_HYBRID, "bad greedy mode");
     if (mode == DLRA_GREEDY_DATA) DLRA_REQUIRE(!h->rhs.set, "DLRA_GREEDY_DATA is defined for data problems");
     else DLRA_REQUIRE(h->rhs.set, "DLRA_GREEDY_HYBRID needs the right-hand side of the Z-flow (dlra_rhs_set)");
+    StepGuard guard(h);
     Delta x = begin_data_step(h, true);
     greedy_two_factor_step(h, x, mode, carry_fsal != 0, t, dt);
     end_data_step(h);
+    guard.commit();
     DLRA_API_END(h)
 }
 
@@ -861,7 +974,16 @@ extern "C" int dlra_set_substepper(dlra_handle h, int flow, int ode, int nsub, d
     c.ode = ode; c.nsub = nsub;
     if (abstol > 0) c.abstol = abstol;
     if (reltol > 0) c.reltol = reltol;
+    c.maxiters = h->sub[flow].maxiters;
     h->sub[flow] = c;
+    DLRA_API_END(h)
+}
+
+extern "C" int dlra_set_substepper_maxiters(dlra_handle h, int flow, int64_t maxiters) {
+    DLRA_API_BEGIN(h)
+    DLRA_REQUIRE(flow >= 0 && flow <= 2, "flow must be DLRA_FLOW_K|S|L");
+    DLRA_REQUIRE(maxiters >= 1, "maxiters >= 1");
+    h->sub[flow].maxiters = maxiters;
     DLRA_API_END(h)
 }
 
@@ -990,6 +1112,31 @@ extern "C" int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass
     }
     h->pass_events.clear();
     h->pass_event_kind.clear();
+    if (!h->phase_marks.empty()) {
+        // marks named "step" open a step; every other mark closes a phase
+        std::vector<std::pair<std::string, double>> acc;
+        int steps = 0;
+        for (size_t i = 0; i < h->phase_marks.size(); ++i) {
+            const char* nm = h->phase_marks[i].first;
+            if (strcmp(nm, "step") == 0) { ++steps; continue; }
+            if (i == 0) continue;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->phase_marks[i - 1].second, h->phase_marks[i].second);
+            bool found = false;
+            for (auto& a : acc) if (a.first == nm) { a.second += ms; found = true; break; }
+            if (!found) acc.emplace_back(nm, ms);
+        }
+        if (reset == 0 || getenv("DLRA_PHASES_ALWAYS")) {
+            int dev = 0; cudaGetDevice(&dev);
+            double tot = 0; for (auto& a : acc) tot += a.second;
+            fprintf(stderr, "[dlra phases] device %d rank %d/%d: %d steps, %.1f us/step on the main stream:", dev, h->comm.rank, h->comm.nranks,
+                    steps, steps ? tot * 1e3 / steps : 0.0);
+            for (auto& a : acc) fprintf(stderr, " %s %.1f", a.first.c_str(), steps ? a.second * 1e3 / steps : 0.0);
+            fprintf(stderr, "\n");
+        }
+        for (auto& pm : h->phase_marks) cudaEventDestroy(pm.second);
+        h->phase_marks.clear();
+    }
     if (kernel_launches) *kernel_launches = h->cx.launches + h->ax.launches;
     if (pass_launches) *pass_launches = h->pass_launches;
     if (pass_ms_total) *pass_ms_total = h->pass_ms;

@@ -37,6 +37,7 @@ struct SubStepperCfg {
     int ode = DLRA_ODE_TSIT5;
     int nsub = 1;
     double abstol = 1e-6, reltol = 1e-3;
+    int64_t maxiters = 100000;   // OrdinaryDiffEq's default `maxiters` (sub-steps incl. rejected ones per `step!(I, dt, true)`)
     // adaptive controller state carried across outer steps (mirrors oracle.SubStepper)
     double dt_next = -1.0;
     double qold = 1e-4;
@@ -100,6 +101,12 @@ struct dlra_engine {
     // software pipelining of the BUG step (pass_tri.cuh): ΔA·V0 already sits in UB and the per-CTA partials of ΔAᵀ·U0 in `part`
     bool kl_ready = false; int kl_nparts = 0; int64_t kl_ldlp = 0; int kl_rank = 0;
 
+    // asynchronous factor snapshots (dlra_save_factors_async): two device staging slots, D2H on the copy stream
+    dlra::DevBuf save_stage[2];
+    cudaEvent_t save_staged[2] = {nullptr, nullptr};   // compute stream: staging copy of slot i complete
+    cudaEvent_t save_landed[2] = {nullptr, nullptr};   // copy stream: D2H of slot i complete (the slot may be overwritten)
+    int save_next = 0;
+
     // DE problems
     dlra::RhsCfg rhs;
     dlra::SubStepperCfg sub[3];
@@ -114,9 +121,24 @@ struct dlra_engine {
     int64_t kind_launches[4] = {0, 0, 0, 0};
     double kind_ms[4] = {0, 0, 0, 0}, kind_bytes[4] = {0, 0, 0, 0}, kind_flops[4] = {0, 0, 0, 0};
     cudaEvent_t user_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // step progress (dlra_progress): one event per step in a ring, polled without blocking
+    static constexpr int NPROG = 64;
+    cudaEvent_t prog_ev[NPROG] = {};
+    int64_t steps_enqueued = 0, steps_completed = 0;
+    // DLRA_PHASES=1: CUDA-event marks at the phase boundaries of a step on the main stream; the per-phase means are printed to
+    // stderr by dlra_stats (the time between two marks is attributed to the later one)
+    bool phase_timing = false;
+    std::vector<std::pair<const char*, cudaEvent_t>> phase_marks;
 };
 
 namespace dlra {
+inline void phase_mark(dlra_engine* e, const char* name) {
+    if (!e->phase_timing) return;
+    cudaEvent_t ev;
+    DLRA_CUDA(cudaEventCreate(&ev));
+    DLRA_CUDA(cudaEventRecord(ev, e->cx.stream));
+    e->phase_marks.emplace_back(name, ev);
+}
 inline void pass_timer_begin(dlra_engine* e, double bytes, int kind = 1, double flops = 0.0) {
     e->pass_launches++;
     e->pass_bytes += bytes;

@@ -562,13 +562,15 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
 inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, int64_t ldlp, int rt, int csize, const double* Vi,
                        int64_t ldvi, const double* Si, int64_t ldsi, int rk, double* L, int64_t ldl, Ctx* on = nullptr) {
     const int64_t part_stride = ldlp * rt * csize;
-    Ctx& cx = on ? *on : e->cx;   // single-GPU runs may place this L-side kernel on the auxiliary stream
+    Ctx& cx = on ? *on : e->cx;   // the L-side tail may run on the auxiliary stream beside the K-side chain
     Comm& cm = e->comm;
-    DLRA_REQUIRE(on == nullptr || cm.nranks <= 1, "collectives stay on the main stream");
+    DLRA_REQUIRE(on == nullptr || cm.nranks <= 1 || cm.p2p, "library collectives stay on the main stream");
+    const int chan = on ? 1 : 0;  // the auxiliary stream owns exchange channel 1 (channel 0: collectives of the main stream)
     const int64_t total = e->m * (int64_t)rc;
     // the cross-rank variant spins on peer flags, so its whole grid must be co-resident (256 threads, <= 16 KB smem: >= 4 CTAs/SM)
     const bool xr = cm.nranks > 1 && cm.p2p;
-    const int grid = (int)std::min<int64_t>(cdiv(total, 256), xr ? 4 * (int64_t)cx.num_sms : ((int64_t)1 << 30));
+    // (on the auxiliary stream the spinning CTAs must leave whole SMs to the K-side TSQR that runs beside them)
+    const int grid = (int)std::min<int64_t>(cdiv(total, 256), xr ? (on ? (int64_t)cx.num_sms / 2 : 4 * (int64_t)cx.num_sms) : ((int64_t)1 << 30));
     const int s_in_smem = (size_t)rc * rk * sizeof(double) <= 40 * 1024 ? 1 : 0;
     const size_t smem = (Vi && s_in_smem) ? (size_t)rc * rk * sizeof(double) : 0;
     if (cm.nranks <= 1) {
@@ -576,8 +578,8 @@ inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, i
         cx.launches++;
     } else if (cm.p2p) {
         DLRA_REQUIRE((size_t)total * 8 <= cm.xdata_bytes, "P2P exchange region too small for an L chunk");
-        P2PView v = cm.next_view();
-        l_finalize_kernel<true><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, v, cm.ticket, s_in_smem);
+        P2PView v = cm.next_view(chan);
+        l_finalize_kernel<true><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, v, cm.ticket_of(chan), s_in_smem);
         cx.launches++;
     } else {
         // NCCL transport: local reduction, library all-reduce of the dense chunk (ldl == m), then the initial term

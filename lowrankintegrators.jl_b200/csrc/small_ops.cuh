@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(128) gemm_nn_kernel(int64_t n, int p, int q, c
                                                        const double* __restrict__ Aprev, int64_t ldap,
                                                        const double* __restrict__ B, int64_t ldb, int transB,
                                                        double* __restrict__ C, int64_t ldc, double alpha, double beta) {
-    constexpr int KT = 64;
+    constexpr int KT = QC >= 64 ? 32 : 64;
     __shared__ double Bs[KT][QC];
     const int64_t i = (int64_t)blockIdx.x * 128 + threadIdx.x;
     const int c0 = blockIdx.y * QC;
@@ -57,8 +57,17 @@ __global__ void __launch_bounds__(128) gemm_nn_kernel(int64_t n, int p, int q, c
 inline void gemm_nn(Ctx& cx, int64_t n, int p, int q, const double* A, int64_t lda, const double* Aprev, int64_t ldap,
                     const double* B, int64_t ldb, bool transB, double* C, int64_t ldc, double alpha, double beta) {
     if (n <= 0 || q <= 0) return;
-    dim3 grid((unsigned)cdiv(n, 128), (unsigned)cdiv(q, 16));
-    gemm_nn_kernel<16><<<grid, 128, 0, cx.stream>>>(n, p, q, A, lda, Aprev, ldap, B, ldb, transB ? 1 : 0, C, ldc, alpha, beta);
+    // wide outputs keep all q accumulators of a row in one thread so that A is streamed once (not once per 16 columns)
+    if (q > 32 && n >= 8192) {
+        dim3 grid((unsigned)cdiv(n, 128), (unsigned)cdiv(q, 64));
+        gemm_nn_kernel<64><<<grid, 128, 0, cx.stream>>>(n, p, q, A, lda, Aprev, ldap, B, ldb, transB ? 1 : 0, C, ldc, alpha, beta);
+    } else if (q > 16 && n >= 8192) {
+        dim3 grid((unsigned)cdiv(n, 128), (unsigned)cdiv(q, 32));
+        gemm_nn_kernel<32><<<grid, 128, 0, cx.stream>>>(n, p, q, A, lda, Aprev, ldap, B, ldb, transB ? 1 : 0, C, ldc, alpha, beta);
+    } else {
+        dim3 grid((unsigned)cdiv(n, 128), (unsigned)cdiv(q, 16));
+        gemm_nn_kernel<16><<<grid, 128, 0, cx.stream>>>(n, p, q, A, lda, Aprev, ldap, B, ldb, transB ? 1 : 0, C, ldc, alpha, beta);
+    }
     cx.launches++;
     DLRA_CUDA(cudaGetLastError());
 }
@@ -209,6 +218,131 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q,
     if (threadIdx.x == 0) counters[slot] = 0;   // self-reset for the next launch on this stream
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Wide Gram-type product (p or q > 16, long n) on the fp64 tensor pipe, ONE launch, A and B streamed ONCE per 64 x 64 output
+// block:  a persistent CTA per SM owns a contiguous range of 32-row tiles, stages [32 rows x 64 cols] of A and of B through a
+// 4-deep cp.async ring (column stride 36 doubles: both DMMA fragment patterns are bank-conflict free) and its 8 warps
+// (2 x 4, 32 x 16 outputs each) run DMMA.8x8x4 over them.  Per-CTA partials are reduced in fixed order by the last CTA
+// (ticket counter) — deterministic, no atomics on data.  Needs 16-byte aligned column starts (even lda/ldb).
+// ------------------------------------------------------------------------------------------------
+constexpr int GT_ROWS = 32, GT_LD = 36, GT_BLK = 64, GT_STAGES = 4;
+constexpr int GT_TILE_DOUBLES = GT_BLK * GT_LD;                                   // one operand tile
+constexpr int GT_SMEM_BYTES = GT_STAGES * 2 * GT_TILE_DOUBLES * (int)sizeof(double);   // 147456
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t d = smem_u32(smem_dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(256, 1) gram_tile_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
+                                                           const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
+                                                           double alpha, double beta, double* __restrict__ part,
+                                                           unsigned int* __restrict__ counters, int64_t tiles_per_cta) {
+    extern __shared__ __align__(16) double gts[];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;          // warp tile: rows [32 wm, +32) x cols [16 wn, +16) of the 64 x 64 block
+    const int a0 = blockIdx.y * GT_BLK, b0 = blockIdx.z * GT_BLK;
+    const int64_t ntiles = (n + GT_ROWS - 1) / GT_ROWS;
+    const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = min(ntiles, t0 + tiles_per_cta);
+    double acc[4][2][2];
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+
+    // loader: a tile is 64 columns x 16 chunks of 16 bytes; thread -> (column = e / 16, chunk = e % 16), 4 chunks per operand
+    auto issue = [&](int64_t t, int stage) {
+        double* As = gts + (size_t)stage * 2 * GT_TILE_DOUBLES;
+        double* Bs = As + GT_TILE_DOUBLES;
+        const int64_t r0 = t * GT_ROWS;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int e = threadIdx.x + it * 256;
+            const int col = e >> 4, ch = e & 15;
+            const int64_t row = r0 + 2 * ch;
+            const bool rok = row < n;   // n even or the tail element is zero-filled below
+            const bool aok = rok && (a0 + col) < p, bok = rok && (b0 + col) < q;
+            const double* ga = A + (aok ? row + (int64_t)(a0 + col) * lda : 0);
+            const double* gb = B + (bok ? row + (int64_t)(b0 + col) * ldb : 0);
+            cp_async16_zfill(As + col * GT_LD + 2 * ch, ga, aok);
+            cp_async16_zfill(Bs + col * GT_LD + 2 * ch, gb, bok);
+        }
+    };
+    const int64_t my = t1 > t0 ? t1 - t0 : 0;
+#pragma unroll
+    for (int s = 0; s < GT_STAGES - 1; ++s) {
+        if (s < my) issue(t0 + s, s);
+        cp_async_commit();
+    }
+    for (int64_t i = 0; i < my; ++i) {
+        cp_async_wait<GT_STAGES - 2>();
+        __syncthreads();                       // tile i landed for everybody; everybody is done with tile i-1's slot
+        if (i + GT_STAGES - 1 < my) issue(t0 + i + GT_STAGES - 1, (int)((i + GT_STAGES - 1) % GT_STAGES));
+        cp_async_commit();
+        const double* As = gts + (size_t)(i % GT_STAGES) * 2 * GT_TILE_DOUBLES;
+        const double* Bs = As + GT_TILE_DOUBLES;
+        const double* ap = As + (wm * 32 + g) * GT_LD + k;
+        const double* bp = Bs + (wn * 16 + g) * GT_LD + k;
+#pragma unroll
+        for (int ks = 0; ks < GT_ROWS / 4; ++ks) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb) af[mb] = ap[mb * 8 * GT_LD + ks * 4];
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) bf[nb] = bp[nb * 8 * GT_LD + ks * 4];
+#pragma unroll
+            for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < 2; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+        }
+    }
+    cp_async_wait<0>();
+    // an odd n leaves the last element of a 16-byte chunk beyond the matrix: it was loaded (aligned chunk inside the padded
+    // column) only when row+1 < n is guaranteed by the host-side check n % 2 == 0
+    const int nblk = gridDim.x;
+    const int slot = blockIdx.y * gridDim.z + blockIdx.z;
+    double* mypart = part + ((int64_t)slot * nblk + blockIdx.x) * (GT_BLK * GT_BLK);
+#pragma unroll
+    for (int mb = 0; mb < 4; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e)
+                mypart[(wm * 32 + mb * 8 + g) + GT_BLK * (wn * 16 + nb * 8 + 2 * k + e)] = acc[mb][nb][e];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&counters[slot], 1u);
+        is_last = (ticket == (unsigned int)nblk - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double* base = part + (int64_t)slot * nblk * (GT_BLK * GT_BLK);
+    for (int e = threadIdx.x; e < GT_BLK * GT_BLK; e += 256) {
+        const int i = e % GT_BLK, j = e / GT_BLK;
+        if (a0 + i >= p || b0 + j >= q) continue;
+        double s = 0.0;
+        for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * (GT_BLK * GT_BLK) + e);
+        double* dst = C + (a0 + i) + (int64_t)(b0 + j) * ldc;
+        *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
+    }
+    if (threadIdx.x == 0) counters[slot] = 0;
+}
+
+inline bool gram_tile_ok(const Ctx& cx, int64_t n, int p, int q, const double* A, int64_t lda, const double* B, int64_t ldb) {
+    if (cx.counters == nullptr || n < 8192 || (p <= 16 && q <= 16)) return false;
+    if (cdiv(p, GT_BLK) * cdiv(q, GT_BLK) > 256) return false;
+    return (n % 2) == 0 && (lda % 2) == 0 && (ldb % 2) == 0 && (((uintptr_t)A) & 15) == 0 && (((uintptr_t)B) & 15) == 0;
+}
+inline int gram_tile_ctas(const Ctx& cx, int64_t n) { return (int)std::min<int64_t>(cx.num_sms, cdiv(n, GT_ROWS)); }
+
 // workspace (doubles) needed by gemm_tn for the partial sums
 inline int64_t gemm_tn_chunks(const Ctx& cx, int64_t n, int p, int q) {
     int64_t blocks = cdiv(p, 32) * cdiv(q, 32);
@@ -221,13 +355,26 @@ inline bool gram_fast_ok(const Ctx& cx, int p, int q) { return cx.counters != nu
 inline int64_t gemm_tn_ws(const Ctx& cx, int64_t n, int p, int q) {
     const int64_t generic = gemm_tn_chunks(cx, n, p, q) * p * q;
     const int64_t fast = cdiv(p, 16) * cdiv(q, 16) * cdiv(n, GRAM_ROWS_PER_CTA) * 256;
-    return std::max(generic, fast);
+    const int64_t tiled = cdiv(p, GT_BLK) * cdiv(q, GT_BLK) * (int64_t)gram_tile_ctas(cx, n) * GT_BLK * GT_BLK;
+    return std::max(std::max(generic, fast), tiled);
 }
 
 // C[p x q] = beta*C + alpha * (A - Aprev)' * B
 inline void gemm_tn(Ctx& cx, int64_t n, int p, int q, const double* A, int64_t lda, const double* Aprev, int64_t ldap,
                     const double* B, int64_t ldb, double* C, int64_t ldc, double alpha, double beta, double* ws) {
     if (p <= 0 || q <= 0) return;
+    if (!Aprev && gram_tile_ok(cx, n, p, q, A, lda, B, ldb)) {
+        static unsigned long long attr_devs = 0;
+        if (first_use_on_this_device(attr_devs))
+            DLRA_CUDA(cudaFuncSetAttribute(gram_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+        const int G = gram_tile_ctas(cx, n);
+        const int64_t tiles_per_cta = cdiv(cdiv(n, GT_ROWS), G);
+        dim3 grid((unsigned)G, (unsigned)cdiv(p, GT_BLK), (unsigned)cdiv(q, GT_BLK));
+        gram_tile_kernel<<<grid, 256, GT_SMEM_BYTES, cx.stream>>>(n, p, q, A, lda, B, ldb, C, ldc, alpha, beta, ws, cx.counters, tiles_per_cta);
+        cx.launches++;
+        DLRA_CUDA(cudaGetLastError());
+        return;
+    }
     if (!Aprev && gram_fast_ok(cx, p, q)) {
         dim3 grid((unsigned)cdiv(n, GRAM_ROWS_PER_CTA), (unsigned)cdiv(p, 16), (unsigned)cdiv(q, 16));
         gram_dmma_kernel<<<grid, 256, 0, cx.stream>>>(n, p, q, A, lda, B, ldb, C, ldc, alpha, beta, ws, cx.counters);

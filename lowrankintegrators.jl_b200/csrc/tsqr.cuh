@@ -58,8 +58,10 @@ struct TReduce<1, OFF> {
 // then rotates the register columns by two, so the pivots are always positions 0 and 1.  The finished column j (R above/on
 // the diagonal, the Householder vector below it, unit diagonal implicit) is parked in shared memory `vs` ([CP][vld],
 // lane <-> row), tau[] as LAPACK dlarfg.  One transposing reduction per column yields the norm and all trailing dots.
+// `bc`: 2*CP doubles of warp-private shared memory: the reduced dot products and the pivot row are BROADCAST through it
+// (a few LDS per lane) instead of two shuffles per trailing column — the shuffle unit was the busiest pipe of this routine.
 template <int CP, int RPL>
-__device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, int vld, double* tau_s, int lane) {
+__device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, int vld, double* tau_s, int lane, double* bc) {
     constexpr int SH = (CP == 16) ? 1 : 2;   // owner lane of reduced value i is i << SH
 #pragma unroll 1
     for (int j0 = 0; j0 < CP; j0 += 2) {
@@ -80,8 +82,14 @@ __device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, i
                 e[c] = s;
             }
             const double h = TReduce<CP, 16>::run(e, lane);
-            const double alpha = __shfl_sync(0xffffffffu, a[0][P], j);
-            const double ss = __shfl_sync(0xffffffffu, h, 0);
+            if ((lane & ((1 << SH) - 1)) == 0) bc[lane >> SH] = h;          // value i lives on lanes i << SH ..
+            if (lane == j) {
+#pragma unroll
+                for (int c = P; c < CP; ++c) bc[CP + c] = a[0][c];           // pivot row of the trailing block
+            }
+            __syncwarp();
+            const double alpha = bc[CP + P];
+            const double ss = bc[0];
             double t = 0.0, scale = 0.0, beta = alpha;
             if (ss > 0.0) {
                 // dlarfg with one rsqrt and one reciprocal on the dependent chain: beta = -sign(alpha)*||x||,
@@ -105,12 +113,13 @@ __device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, i
             // apply H_j to the trailing columns
 #pragma unroll
             for (int c = P + 1; c < CP; ++c) {
-                const double arow = __shfl_sync(0xffffffffu, a[0][c], j);
-                const double ec = __shfl_sync(0xffffffffu, h, (c - P) << SH);
+                const double arow = bc[CP + c];
+                const double ec = bc[c - P];
                 const double w = (arow + ec * scale) * t;
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) a[q][c] = fma(-w, vm[q], a[q][c]);
             }
+            __syncwarp();   // bc is rewritten by the next column
         });
         // rotate two positions to the left
 #pragma unroll
@@ -126,7 +135,7 @@ __device__ __forceinline__ void reg_panel_qr(double (&a)[RPL][CP], double* vs, i
 // Explicit thin Q (32*RPL x CP) into registers from the vectors parked by reg_panel_qr (LAPACK dorg2r recurrence, looped,
 // two columns per trip with rotating register columns: position c holds Q column j_low + c).
 template <int CP, int RPL>
-__device__ __forceinline__ void reg_panel_formq(double (&a)[RPL][CP], const double* vs, int vld, const double* tau_s, int lane) {
+__device__ __forceinline__ void reg_panel_formq(double (&a)[RPL][CP], const double* vs, int vld, const double* tau_s, int lane, double* bc) {
     constexpr int SH = (CP == 16) ? 1 : 2;
 #pragma unroll
     for (int c = 0; c < CP; ++c)
@@ -157,13 +166,16 @@ __device__ __forceinline__ void reg_panel_formq(double (&a)[RPL][CP], const doub
                 e[c] = s;
             }
             const double h = TReduce<CP, 16>::run(e, lane);
+            if ((lane & ((1 << SH) - 1)) == 0) bc[lane >> SH] = h;
+            __syncwarp();
             if (lane == j) vm[0] = 1.0;    // row j of the finished columns is still 0: the same FMA writes -w there
 #pragma unroll
             for (int c = P + 1; c < CP; ++c) {
-                const double w = __shfl_sync(0xffffffffu, h, (c - P - 1) << SH) * t;
+                const double w = bc[c - P - 1] * t;
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) a[q][c] = fma(-w, vm[q], a[q][c]);
             }
+            __syncwarp();
 #pragma unroll
             for (int q = 0; q < RPL; ++q) a[q][P] = -t * vm[q];
             if (lane == j) a[0][P] = 1.0 - t;
@@ -177,12 +189,13 @@ struct TsqrSmem {
     static constexpr int PROWS = 32 * TSQR_RPL0;               // rows of a level-0 panel
     static constexpr size_t STACK = (size_t)CP * (SROWS + 1);  // doubles
     static constexpr size_t PARK = (size_t)TSQR_NW * CP * PROWS;
-    static constexpr size_t BYTES = (2 * STACK + PARK + (size_t)TSQR_NW * CP) * sizeof(double);
+    static constexpr size_t BCAST = (size_t)TSQR_NW * 2 * CP;   // per-warp broadcast scratch of the panel routines
+    static constexpr size_t BYTES = (2 * STACK + PARK + (size_t)TSQR_NW * CP + BCAST) * sizeof(double);
 };
 
 // warp 0: factor the NW*CP x CP stack of R factors (in shared memory), write R to global and leave the explicit Q in place.
 template <int CP>
-__device__ __noinline__ void tsqr_level1(double* stack, double* stack2, double* taus, double* Rout, int64_t ldr, int lane) {
+__device__ __noinline__ void tsqr_level1(double* stack, double* stack2, double* taus, double* Rout, int64_t ldr, int lane, double* bc) {
     constexpr int RPL1 = TSQR_NW * CP / 32;
     constexpr int SLD = TSQR_NW * CP + 1;
     double b[RPL1][CP];
@@ -190,12 +203,12 @@ __device__ __noinline__ void tsqr_level1(double* stack, double* stack2, double* 
     for (int c = 0; c < CP; ++c)
 #pragma unroll
         for (int q = 0; q < RPL1; ++q) b[q][c] = stack[c * SLD + lane + 32 * q];
-    reg_panel_qr<CP, RPL1>(b, stack2, SLD, taus, lane);
+    reg_panel_qr<CP, RPL1>(b, stack2, SLD, taus, lane, bc);
     if (lane < CP) {
 #pragma unroll
         for (int c = 0; c < CP; ++c) Rout[lane + (int64_t)c * ldr] = (lane <= c) ? stack2[c * SLD + lane] : 0.0;
     }
-    reg_panel_formq<CP, RPL1>(b, stack2, SLD, taus, lane);
+    reg_panel_formq<CP, RPL1>(b, stack2, SLD, taus, lane, bc);
 #pragma unroll
     for (int c = 0; c < CP; ++c)
 #pragma unroll
@@ -223,7 +236,9 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows,
     double* stack2 = stack + SM::STACK;           // [CP][SLD]: Householder vectors of the level-1 factorisation
     double* park = stack2 + SM::STACK;            // [NW][CP][PROWS]: per warp: Householder vectors, then the explicit level-0 Q
     double* taus = park + SM::PARK;               // [NW][CP]
+    double* bcast = taus + TSQR_NW * CP;          // [NW][2*CP]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* bc = bcast + warp * 2 * CP;
     const int64_t row0 = (int64_t)blockIdx.x * TSQR_BR + warp * PROWS;
     double* mypark = park + (size_t)warp * CP * PROWS;
     {
@@ -259,13 +274,13 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows,
             }
             __syncthreads();   // the stack area is reused for the R factors below
         }
-        reg_panel_qr<CP, RPL0>(a, mypark, PROWS, taus + warp * CP, lane);
+        reg_panel_qr<CP, RPL0>(a, mypark, PROWS, taus + warp * CP, lane, bc);
         // R_w -> rows [CP*warp, CP*warp + CP) of the stack (zeros below the diagonal)
         if (lane < CP) {
 #pragma unroll
             for (int c = 0; c < CP; ++c) stack[c * SLD + CP * warp + lane] = (lane <= c) ? mypark[c * PROWS + lane] : 0.0;
         }
-        reg_panel_formq<CP, RPL0>(a, mypark, PROWS, taus + warp * CP, lane);
+        reg_panel_formq<CP, RPL0>(a, mypark, PROWS, taus + warp * CP, lane, bc);
         __syncwarp();
 #pragma unroll
         for (int c = 0; c < CP; ++c)
@@ -273,7 +288,7 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows,
             for (int q = 0; q < RPL0; ++q) mypark[c * PROWS + lane + 32 * q] = a[q][c];
     }
     __syncthreads();
-    if (warp == 0) tsqr_level1<CP>(stack, stack2, taus, Rstack + (int64_t)blockIdx.x * CP, ldr, lane);
+    if (warp == 0) tsqr_level1<CP>(stack, stack2, taus, Rstack + (int64_t)blockIdx.x * CP, ldr, lane, bc);
     __syncthreads();
     // Q_w <- Q_w * X_w,  X_w = rows [CP*warp, +CP) of the explicit level-1 Q
 #pragma unroll 1
@@ -301,6 +316,7 @@ __global__ void __launch_bounds__(32, 1) tsqr_small_kernel(int rows, int C, cons
     constexpr int RPL = 4;
     __shared__ double vs[CP][32 * RPL];
     __shared__ double taus[CP];
+    __shared__ double bc[2 * CP];
     const int lane = threadIdx.x;
     double a[RPL][CP];
 #pragma unroll
@@ -310,12 +326,12 @@ __global__ void __launch_bounds__(32, 1) tsqr_small_kernel(int rows, int C, cons
             const int g = lane + 32 * q;
             a[q][c] = (g < rows && c < C) ? A[g + (int64_t)c * lda] : 0.0;
         }
-    reg_panel_qr<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane);
+    reg_panel_qr<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane, bc);
     if (lane < CP) {
 #pragma unroll
         for (int c = 0; c < CP; ++c) Rout[lane + (int64_t)c * ldr] = (lane <= c) ? vs[c][lane] : 0.0;
     }
-    reg_panel_formq<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane);
+    reg_panel_formq<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane, bc);
 #pragma unroll
     for (int c = 0; c < CP; ++c)
 #pragma unroll
@@ -323,6 +339,52 @@ __global__ void __launch_bounds__(32, 1) tsqr_small_kernel(int rows, int C, cons
             const int g = lane + 32 * q;
             if (g < rows && c < C) Q[g + (int64_t)c * ldq] = a[q][c];
         }
+}
+
+// Cross-rank top of the TSQR tree in ONE single-warp launch (P2P transport): post this rank's R (CP x CP, ld CP) to the exchange
+// region, raise the flag in every peer, wait for the peers, read their R factors straight into the register panel
+// (rows g*CP.. of the stacked G*CP x CP matrix, over NVLink), factor it, and write the replicated R plus THIS rank's CP x CP
+// block of the explicit Q.  Every rank factors the same stack in the same order => bit-identical R on all ranks.
+template <int CP>
+__global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, const double* __restrict__ Rloc, double* __restrict__ Rout,
+                                                          double* __restrict__ Xout) {
+    constexpr int RPL = 4;   // G*CP <= 128 rows
+    __shared__ double vs[CP][32 * RPL];
+    __shared__ double taus[CP];
+    __shared__ double bc[2 * CP];
+    const int lane = threadIdx.x;
+    for (int e = lane; e < CP * CP; e += 32) v.data_local[e] = Rloc[e];
+    __syncwarp();
+    __threadfence_system();
+    if (lane < v.nranks) st_release_sys(v.flags_peer[lane] + (size_t)v.rank * P2P_FLAG_STRIDE, v.seq);
+    if (lane < v.nranks) {
+        const unsigned long long* f = v.flags_local + (size_t)lane * P2P_FLAG_STRIDE;
+        while (ld_acquire_sys(f) < v.seq) { }
+    }
+    __syncwarp();
+    const int rows = v.nranks * CP;
+    double a[RPL][CP];
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+        const int gr = lane + 32 * q;
+        const int g = gr / CP, i = gr % CP;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) a[q][c] = (gr < rows) ? ld_relaxed_sys(v.data_peer[g < v.nranks ? g : 0] + i + c * CP) : 0.0;
+    }
+    reg_panel_qr<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane, bc);
+    if (lane < CP) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) Rout[lane + c * CP] = (lane <= c) ? vs[c][lane] : 0.0;
+    }
+    reg_panel_formq<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane, bc);
+#pragma unroll
+    for (int q = 0; q < RPL; ++q) {
+        const int gr = lane + 32 * q;
+        if (gr >= v.rank * CP && gr < (v.rank + 1) * CP) {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) Xout[(gr - v.rank * CP) + c * CP] = a[q][c];
+        }
+    }
 }
 
 // Q[rows of block b, :C] <- Q[block b, :C] * X_b[:C,:C],  X_b = Xstack[b*xstride .. , :] (ldx); block = block_rows rows.
@@ -421,7 +483,19 @@ inline void tsqr(Ctx& cx, Comm& comm, int64_t rows, int C, const double* A, int6
     double* tail = ws + tsqr_ws_size(rows, C, comm.nranks) - 1024 - (int64_t)(comm.nranks + 1) * CP * CP * 4;
     double* Rloc = tsqr_local(cx, rows, C, A, lda, Q, ldq, ws, add);
     const double* Rfin = Rloc;
-    if (comm.nranks > 1) {
+    if (comm.nranks > 1 && comm.p2p) {
+        DLRA_REQUIRE(comm.nranks * CP <= 128, "too many ranks for the single-warp cross-rank R reduction");
+        DLRA_REQUIRE((size_t)CP * CP * 8 <= comm.xdata_bytes, "P2P exchange region too small for an R factor");
+        double* Rg = tail;                 // CP x CP replicated R
+        double* X = tail + CP * CP;        // this rank's block of the stacked Q
+        P2PView v = comm.next_view(0);
+        if (CP == 8) tsqr_xrank_kernel<8><<<1, 32, 0, cx.stream>>>(v, Rloc, Rg, X);
+        else tsqr_xrank_kernel<16><<<1, 32, 0, cx.stream>>>(v, Rloc, Rg, X);
+        cx.launches++;
+        DLRA_CUDA(cudaGetLastError());
+        apply_blocks(cx, CP, rows, C, Q, ldq, (int64_t)1 << 62, X, CP, 0);
+        Rfin = Rg;
+    } else if (comm.nranks > 1) {
         const int G = comm.nranks;
         double* gathered = tail;                                // G blocks of CP x CP (each ld = CP)
         double* stacked = gathered + (int64_t)G * CP * CP;      // (G*CP) x CP, ld = G*CP

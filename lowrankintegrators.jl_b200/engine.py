@@ -66,11 +66,15 @@ class Engine:
         self.h = h
         self.rmax = int(rmax)
         self._keep = {}
+        # borrowed device snapshots: (index of the step that reads them last, tensor), released by GPU progress (dlra_progress)
+        self._held = []
+        self._npush = 0
 
     def close(self):
         if getattr(self, "h", None):
-            self.lib.dlra_destroy(self.h)
+            self.lib.dlra_destroy(self.h)   # synchronises the engine's streams
             self.h = None
+            self._held = []
 
     def __del__(self):
         try:
@@ -80,6 +84,28 @@ class Engine:
 
     def _ck(self, rc):
         L.check(self.h, rc)
+
+    MAX_RUN_AHEAD = 8   # steps the host may enqueue beyond the device's progress while it feeds borrowed device snapshots
+
+    def progress(self, wait_for=-1):
+        """(steps enqueued, steps completed on the device); blocks until `wait_for` steps are complete if given."""
+        enq, done = C.c_int64(), C.c_int64()
+        self._ck(self.lib.dlra_progress(self.h, C.byref(enq), C.byref(done), int(wait_for)))
+        return enq.value, done.value
+
+    def _borrow(self, keep, last_reader_step):
+        """A device tensor the engine reads asynchronously (dlra.h: a borrowed snapshot must stay valid until the step after the
+        next push has RUN).  The steps are asynchronous and the host may be several steps ahead, so the tensor is held here
+        until the device has completed its last reader; torch's caching allocator can then not hand its memory to a
+        later y(t) while a queued step still reads it.  Also bounds the host's run-ahead (and with it the held memory)."""
+        if not (_is_torch(keep) and keep.is_cuda):
+            return
+        self._held.append((last_reader_step, keep))
+        enq, done = self.progress()
+        if enq - done > self.MAX_RUN_AHEAD:
+            enq, done = self.progress(wait_for=enq - self.MAX_RUN_AHEAD)
+        while self._held and self._held[0][0] <= done:
+            self._held.pop(0)
 
     def _after_torch(self):
         """Device tensors are produced on torch's current stream, the engine runs on its own: make the engine stream wait
@@ -150,6 +176,22 @@ class Engine:
         self._ck(self.lib.dlra_get_factors_host(self.h, U.ctypes.data, self.n, S.ctypes.data, r, V.ctypes.data, self.m, C.byref(rr)))
         return U, S, V
 
+    def save_factors_async(self):
+        """Asynchronous snapshot of the current factors into pinned host memory (dlra_save_factors_async).  Returns
+        (U, S, V) NumPy views (column-major) that are valid after save_wait(); the step stream is not stalled."""
+        r = self.rank
+        bufs = []
+        for rows in (self.n, r, self.m):
+            t = torch.empty((r, rows), dtype=torch.float64, pin_memory=True)   # row-major (r, rows) == column-major (rows, r)
+            bufs.append(t)
+        rr = C.c_int()
+        self._ck(self.lib.dlra_save_factors_async(self.h, bufs[0].data_ptr(), self.n, bufs[1].data_ptr(), r, bufs[2].data_ptr(), self.m,
+                                                  C.byref(rr)))
+        return tuple(b.numpy().T for b in bufs)
+
+    def save_wait(self):
+        self._ck(self.lib.dlra_save_wait(self.h))
+
     def get_factors_device(self):
         r = self.rank
         dev = torch.device("cuda", self.device)
@@ -167,7 +209,10 @@ class Engine:
         self._ck(fn(self.h, p, ld))
         if host:
             self.sync_copies = True
+        self._held.clear()
+        self._npush = self.progress()[0]       # pushes are counted from the current step index
         self._keep["prev"] = keep
+        self._borrow(keep, self._npush + 1)    # yprev is read by the next step only
 
     def data_push(self, A, kind=L.DATA_SNAPSHOT):
         p, ld, host, keep = _ptr_ld(A)
@@ -175,12 +220,15 @@ class Engine:
         if not host:
             self._after_torch()
         self._ck(fn(self.h, p, ld, kind))
-        # borrowed device pointers must outlive the step after next (plus one snapshot of lookahead): keep the last four alive
-        self._keep["cur3"] = (self._keep.get("cur3", ()) + (keep,))[-4:]
+        # the i-th push after data_init serves step i as the current snapshot and step i+1 as the previous one
+        self._npush += 1
+        self._borrow(keep, self._npush + 1)
 
     # -- DE problems -------------------------------------------------------------------------------
-    def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0):
+    def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0, maxiters=None):
         self._ck(self.lib.dlra_set_substepper(self.h, flow, ode, nsub, abstol, reltol))
+        if maxiters is not None:
+            self._ck(self.lib.dlra_set_substepper_maxiters(self.h, flow, int(maxiters)))
 
     @staticmethod
     def _operator(x, keep):

@@ -247,6 +247,10 @@ TSIT5_BTILDE = (-0.00178001105222577714, -0.0008164344596567469, 0.0078808780102
                 0.5823571654525552, -0.45808210592918697, 0.015151515151515152)
 
 
+class MaxItersError(RuntimeError):
+    """OrdinaryDiffEq returns retcode MaxIters (with a warning) when `maxiters` sub-steps do not reach the requested time."""
+
+
 @dataclass
 class SubStepper:
     """Stand-in for the `*_alg` / `*_kwargs` of the algorithm constructors
@@ -257,6 +261,7 @@ class SubStepper:
     nsub: int = 1
     abstol: float = 1e-6
     reltol: float = 1e-3
+    maxiters: int = 100000   # OrdinaryDiffEq default `maxiters` (the reference passes none): MaxItersError beyond it
     # adaptive controller state (carried across outer steps like an OrdinaryDiffEq integrator object)
     dt_next: Optional[float] = None
     qold: float = 1e-4
@@ -333,6 +338,7 @@ def ode_advance(stepper: SubStepper, f, u0, t0, dt, carry: Optional[dict] = None
     assert kind == "tsit5"
     tend = t0 + dt
     t = t0
+    saved = (stepper.dt_next, stepper.qold)   # a failed step leaves the controller as it was (like the engine's StepGuard)
     k1 = first_stage(t)  # FSAL invalidated by set_u! (carry is None) or kept (hybrid Z integrator)
     if stepper.dt_next is None:
         # Hairer-Norsett-Wanner initial step heuristic (order 5)
@@ -348,7 +354,12 @@ def ode_advance(stepper: SubStepper, f, u0, t0, dt, carry: Optional[dict] = None
         stepper.dt_next = min(100.0 * h0, h1, dt)
     h = stepper.dt_next
     beta1, beta2, gamma, qmin, qmax = 7.0 / 50.0, 2.0 / 25.0, 0.9, 0.2, 10.0
+    iters = 0
     while (tend - t) > 1e-14 * max(1.0, abs(tend)):
+        iters += 1
+        if iters > stepper.maxiters:
+            stepper.dt_next, stepper.qold = saved
+            raise MaxItersError("adaptive Tsit5 reached maxiters before the end of the step")
         h = min(h, tend - t)
         unew, ks = _tsit5_stages(f, u, t, h, k1)
         stepper.nfev += 6

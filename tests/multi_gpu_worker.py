@@ -21,7 +21,8 @@ def main():
     failures = []
     for (n, m, r, name) in [(4096, 512, 8, "bug"), (4096, 512, 8, "ksl_primal"), (4096, 512, 8, "ksl_dual"), (6144, 384, 16, "bug"),
                             (4096, 512, 6, "rabug"), (4096, 512, 8, "greedy"), (2050, 130, 5, "bug"),
-                            (4096, 512, 8, "greedy2"), (2050, 130, 5, "greedy2")]:
+                            (4096, 512, 8, "greedy2"), (2050, 130, 5, "greedy2"),
+                            (16384, 384, 40, "bug"), (16384, 384, 24, "ksl_primal")]:
         A = lowrank_stream(n, m, 2 * r if name != "rabug" else 10, seed=21, eps=0.0 if name == "rabug" else 1e-4)
         snaps = [A(0.04 * k) for k in range(4)]
         X0 = O.truncated_svd(snaps[0], r)

@@ -141,3 +141,75 @@ def test_de_solve_matches_oracle_trajectory(lri):
     osol = O.solve(O.MatrixDEProblem(of, X0, (0.0, 0.2)), O.ProjectorSplitting(O.PrimalLieTrotter()), 0.01)
     assert len(sol.Y) == len(osol.Y) and abs(sol.t[-1] - osol.t[-1]) < 1e-12
     assert rel_fro(sol.Y[-1].full(), osol.Y[-1].full()) <= 1e-9
+
+
+def test_reference_burgers_test_config(lri):
+    """test/data_agnostic_approximation.jl as written: n = 1000, m = 20^2, r = 5, dt = 1e-2, the five solvers with their DEFAULT
+    sub-integrators (adaptive Tsit5, abstol 1e-6, reltol 1e-3).  Three steps each against the oracle."""
+    import torch
+    n, mm, r, dt = 1000, 20, 5, 1e-2
+    lap, grad = periodic_ops(n)
+    x = (np.arange(n) + 0.5) * (np.pi / n)
+    ub = 0.5 * (np.exp(np.cos(x)) - 1.5) * np.sin(x + 2 * np.pi * 0.37)
+    xi = [(a, b) for a in np.linspace(-1, 1, mm) for b in np.linspace(-1, 1, mm)]
+    rho0 = np.stack([ub + 0.5 * a * np.sin(2 * np.pi * x) + 0.5 * b * np.sin(3 * np.pi * x) for a, b in xi], axis=1)
+    X0 = O.truncated_svd(rho0, r)
+    of = lambda rho, t: lap @ rho - (grad @ rho) * rho
+    grhs = lri.BurgersRHS(csr_dev(lap), csr_dev(grad))
+    pairs = {
+        "bug": (lri.UnconventionalAlgorithm(), O.UnconventionalAlgorithm()),
+        "ksl_primal": (lri.ProjectorSplitting(lri.PrimalLieTrotter()), O.ProjectorSplitting(O.PrimalLieTrotter())),
+        "ksl_dual": (lri.ProjectorSplitting(lri.DualLieTrotter()), O.ProjectorSplitting(O.DualLieTrotter())),
+        "ksl_strang": (lri.ProjectorSplitting(lri.Strang()), O.ProjectorSplitting(O.Strang())),
+        "rabug": (lri.RankAdaptiveUnconventionalAlgorithm(1e-4, rmax=10), O.RankAdaptiveUnconventionalAlgorithm(1e-4, rmax=10)),
+    }
+    for name, (galg, oalg) in pairs.items():
+        errs = run_both(lri, grhs, of, X0, galg, oalg, dt, 3, resync=True)
+        assert max(errs) <= 1e-9, (name, errs)   # adaptive sub-steppers: accept/reject sequences must coincide
+
+
+def test_stiff_projected_flow_hits_maxiters_like_the_oracle(lri):
+    """BASELINE configs[2] at its stated dt = 1e-2 is outside the explicit sub-stepper's reach once the grid is fine: the
+    discrete Laplacian has |lambda|max = 4 nu / dx^2 (1.36e5 at n = 8192), Tsit5 is stable for h*|lambda| < ~3.5, so one
+    outer step needs > dt*|lambda|/3.5 sub-steps per flow.  OrdinaryDiffEq stops at maxiters (default 1e5) with retcode
+    MaxIters; engine and oracle must do the same thing at the same point, and the engine must stay usable afterwards."""
+    n, mm, r, dt = 2048, 8, 8, 1e-2
+    lap, grad = periodic_ops(n)
+    x = (np.arange(n) + 0.5) * (np.pi / n)
+    ub = 0.5 * (np.exp(np.cos(x)) - 1.5) * np.sin(x + 2 * np.pi * 0.37)
+    xi = [(a, b) for a in np.linspace(-1, 1, mm) for b in np.linspace(-1, 1, mm)]
+    rho0 = np.stack([ub + 0.5 * a * np.sin(2 * np.pi * x) + 0.5 * b * np.sin(3 * np.pi * x) for a, b in xi], axis=1)
+    X0 = O.truncated_svd(rho0, r)
+    of = lambda rho, t: lap @ rho - (grad @ rho) * rho
+    grhs = lri.BurgersRHS(csr_dev(lap), csr_dev(grad))
+    lam = 4 * 0.005 / (np.pi / n) ** 2
+    need = dt * lam / 3.5            # ~24 sub-steps per flow at n = 2048
+    for maxiters, expect_fail in ((int(need // 2), True), (4000, False)):
+        gsub = lambda: lri.SubStepper(maxiters=maxiters)
+        osub = lambda: O.SubStepper(maxiters=maxiters)
+        galg = lri.ProjectorSplitting(lri.PrimalLieTrotter(), K_alg=gsub(), S_alg=gsub(), L_alg=gsub())
+        oalg = O.ProjectorSplitting(O.PrimalLieTrotter(), K_alg=osub(), S_alg=osub(), L_alg=osub())
+        gint = lri.init(lri.MatrixDEProblem(grhs, lri.SVDLikeRepresentation(X0.U, X0.S, X0.V), (0.0, 1.0)), galg, dt)
+        oint = O.init(O.MatrixDEProblem(of, X0, (0.0, 1.0)), oalg, dt)
+        if expect_fail:
+            with pytest.raises(O.MaxItersError):
+                O.step(oint)
+            with pytest.raises(lri._lib.DLRAError) as ei:
+                lri.step(gint)
+            assert ei.value.code == lri._lib.EMAXITERS
+            # the failed step left the factors untouched and the handle usable
+            U, S, V = gint.cache.get_factors()
+            assert rel_fro(U @ S @ V.T, X0.full()) < 1e-14
+            for f in (lri._lib.FLOW_K, lri._lib.FLOW_S, lri._lib.FLOW_L):
+                gint.cache.set_substepper(f, lri._lib.ODE_TSIT5, 1, 1e-6, 1e-3, maxiters=4000)
+            gint.cache.step_ksl(lri._lib.KSL_PRIMAL, 0.0, dt)
+            for s in (oint.cache.K_alg, oint.cache.S_alg, oint.cache.L_alg):
+                s.maxiters = 4000
+            O.step(oint)
+            U, S, V = gint.cache.get_factors()
+            assert rel_fro(U @ S @ V.T, oint.u.full()) <= 1e-9
+        else:
+            O.step(oint)
+            lri.step(gint)
+            assert rel_fro(gint.u.full(), oint.u.full()) <= 1e-9
+        gint.cache.close()

@@ -1,4 +1,4 @@
-"""Full BASELINE-size checks through size-independent properties (the oracle cannot run at these sizes in seconds):
+"""Full BASELINE-size checks: a direct 3-step comparison with the CPU oracle (about 1.3 s per oracle step) and size-independent properties:
 exactness — if rank A(t) <= r, KSL and BUG reproduce A(t_k) to round-off (README refs [1],[2] of the reference) — at
 configs[1] size n=65536, m=4096, r=16 with device-resident snapshots, for the two-pass and the software-pipelined path,
 and pipelined == two-pass on a full-rank perturbed stream."""
@@ -92,3 +92,53 @@ def test_pipelined_equals_two_pass_on_full_rank_stream(setup):
         den += float(torch.sum(Y1 ** 2))
     rel = (num / den) ** 0.5
     assert rel < 1e-10, rel
+
+
+def _blockwise_rel(torch, fa, fb):
+    (U1, S1, V1), (U2, S2, V2) = fa, fb
+    num = den = 0.0
+    US1, US2 = U1 @ S1, U2 @ S2
+    for j0 in range(0, M, 256):
+        Y1 = US1 @ V1[j0:j0 + 256].T
+        Y2 = US2 @ V2[j0:j0 + 256].T
+        num += float(torch.sum((Y1 - Y2) ** 2))
+        den += float(torch.sum(Y2 ** 2))
+    return (num / den) ** 0.5
+
+
+@pytest.mark.parametrize("lookahead", [False, True])
+def test_oracle_parity_at_config2_size(setup, lookahead):
+    """Direct comparison with the CPU oracle at the FULL configs[1] size (65536 x 4096, r = 16, BUG, unconventional.jl:133-157):
+    three steps from the same u0 on the same bytes, two-pass and software-pipelined path, 1e-10 on U*S*V' after every step."""
+    from oracle import dlra_oracle as O
+    lri, torch, snaps, u0 = setup
+    g = torch.Generator(device=snaps[0].device)
+    g.manual_seed(23)
+    noisy = []
+    for A in snaps:
+        B = lri.empty_colmajor(N, M, A.device)
+        B.copy_(A)
+        B.add_(1e-3 * (torch.rand((N, M), generator=g, device=A.device, dtype=torch.float64) - 0.5))
+        noisy.append(B)
+    host = [np.asfortranarray(B.t().cpu().numpy().T) for B in noisy]   # the same bytes, column-major on the host
+    U0, S0, V0 = (x.cpu().numpy() for x in u0)
+    oint = O.init(O.MatrixDataProblem(host, O.SVDLikeRepresentation(U0, S0, V0)), O.UnconventionalAlgorithm(), 1)
+    L = lri._lib
+    eng = lri.Engine(N, M, R)
+    eng.set_factors(*u0)
+    eng.data_init(noisy[0])
+    pushed = 0
+    errs = []
+    for k in range(len(noisy) - 1):
+        if pushed == 0:
+            eng.data_push(noisy[k + 1]); pushed = 1
+        if lookahead and pushed == 1 and k + 2 < len(noisy):
+            eng.data_push(noisy[k + 2]); pushed = 2
+        pushed -= 1
+        eng.step_bug()
+        O.step(oint)
+        gfac = eng.get_factors_device()
+        ofac = tuple(torch.from_numpy(np.ascontiguousarray(x)).to(gfac[0].device) for x in (oint.u.U, oint.u.S, oint.u.V))
+        errs.append(_blockwise_rel(torch, gfac, ofac))
+    eng.close()
+    assert max(errs) <= 1e-10, errs

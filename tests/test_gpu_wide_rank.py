@@ -22,7 +22,7 @@ def lri():
 
 
 @pytest.mark.parametrize("name", ["bug", "ksl_primal", "ksl_dual", "greedy"])
-@pytest.mark.parametrize("shape", [(4096, 512, 64), (2048, 640, 48), (8192, 256, 64), (3072, 384, 32)])
+@pytest.mark.parametrize("shape", [(4096, 512, 64), (2048, 640, 48), (8192, 256, 64), (3072, 384, 32), (16384, 320, 64), (12288, 256, 40)])
 def test_step_parity_wide(lri, name, shape):
     n, m, r = shape
     A = lowrank_stream(n, m, 2 * r, seed=17, eps=1e-4)

@@ -47,7 +47,7 @@ class FakeEngine:
     def rhs_set(self, *a, **k):
         self.calls.append(("rhs_set",))
 
-    def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0):
+    def set_substepper(self, flow, ode, nsub=1, abstol=0.0, reltol=0.0, maxiters=None):
         self.calls.append(("substepper", flow, ode, nsub))
 
     def sync(self):
