@@ -133,7 +133,10 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clocks and throttle reasons DURING the timed region (NVML from a background thread)."""
+    """Samples SM clocks and throttle reasons DURING the timed region (NVML).  NVML queries from a polling thread perturb the
+    measured process (profiles/r02/multi_gpu_phases.txt: a 20 ms poll cost rank 0 ~95 us per 1.4 ms step), so the thread polls
+    at the recipe's 200 ms period and sample() adds one reading from the main thread right after the timed steps have been
+    enqueued, i.e. while the GPU is still executing them."""
 
     def __init__(self, gpu_index):
         import threading
@@ -151,22 +154,26 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _run(self):
+    def sample(self):
         nv = self.nv
+        if nv is None:
+            return
         names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
-        while not self._stop.is_set():
+        try:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
             try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                try:
-                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if mask & bit:
-                        self.reasons.add(k)
+                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
             except Exception:
-                pass
-            self._stop.wait(0.02)
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for k, bit in names.items():
+                if mask & bit:
+                    self.reasons.add(k)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.wait(0.2):
+            self.sample()
 
     def stop(self):
         if self._thr is not None:
@@ -324,11 +331,15 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("DLRA_BENCH_NO_SAMPLER")) else None
     eng.event_record(0)
+    t_host0 = time.perf_counter()
     for i in range(W, W + K):
         step(i)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K   # host time per step of the enqueue loop (throttled to <= 8 steps ahead)
     eng.event_record(1)
+    if sampler:
+        sampler.sample()   # the last timed steps are still running on the device
     ms_total = eng.event_elapsed_ms(0, 1)
     eng.sync()
     torch.cuda.synchronize()
@@ -450,7 +461,7 @@ def run_gpu(args):
         "config": config_dict(world, "libdlra.so"), "roofline": roof, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": gpu_launches, "clocks": clocks,
         "value_counts": "shard-steps/s: N cfg-2 shards stepped together (weak scaling); at N=1 this is configs[1] itself",
-        "steps_per_sec_global": 1e3 / ms_per_step, "cfg5_strong": cfg5,
+        "steps_per_sec_global": 1e3 / ms_per_step, "host_enqueue_ms_per_step": host_enqueue_ms, "cfg5_strong": cfg5,
     }
     print(json.dumps(line))
     if world > 1:

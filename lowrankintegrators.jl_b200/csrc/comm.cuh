@@ -39,6 +39,56 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
     return v;
 }
 
+// ---- "LL" exchange (flag-in-data, the protocol NCCL uses for latency-bound messages): every double travels as ONE 16-byte
+// store {lo32, flag, hi32, flag} written straight into slot [sender][element] of the RECEIVER's buffer over NVLink, and the
+// receiver spins on its own memory until both flags carry the message's sequence number.  No fence, no separate flag
+// round trip, no staging copy: a small all-reduce costs one NVLink write latency instead of ~50 us of
+// fence + release/acquire handshakes (profiles/r02/multi_gpu_phases.txt).
+struct LLView {
+    int nranks, rank;
+    unsigned int seq;            // never 0 (the buffers start zeroed)
+    int64_t cap;                 // elements per sender slot
+    uint4* local;                // this rank's buffer of the current parity: [nranks][cap]
+    uint4* peer[P2P_MAX_RANKS];  // the same buffer in every rank (own included)
+};
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned int seq) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)b), "r"(seq), "r"((unsigned int)(b >> 32)), "r"(seq)
+                 : "memory");
+}
+__device__ __forceinline__ double ll_load(const uint4* p, unsigned int seq) {
+    unsigned int lo, f1, hi, f2;
+    do {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+    } while (f1 != seq || f2 != seq);
+    return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+// element e of this rank's contribution -> every rank's buffer
+__device__ __forceinline__ void ll_push(const LLView& v, int64_t e, double val) {
+    for (int g = 0; g < v.nranks; ++g) ll_store(v.peer[g] + (size_t)v.rank * v.cap + e, val, v.seq);
+}
+// sum over ranks of element e, in rank order (bit-identical on every rank)
+__device__ __forceinline__ double ll_sum(const LLView& v, int64_t e) {
+    double s = 0.0;
+    for (int g = 0; g < v.nranks; ++g) s += ll_load(v.local + (size_t)g * v.cap + e, v.seq);
+    return s;
+}
+// in-place all-reduce of a dense vector: one launch, every thread pushes its elements and then collects the peers' copies
+__global__ void __launch_bounds__(256) ll_allreduce_kernel(LLView v, double* __restrict__ buf, int64_t count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) ll_push(v, e, buf[e]);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) buf[e] = ll_sum(v, e);
+}
+// dst[g*count + i] = rank g's src[i]
+__global__ void __launch_bounds__(256) ll_allgather_kernel(LLView v, const double* __restrict__ src, double* __restrict__ dst, int64_t count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) ll_push(v, e, src[e]);
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count * v.nranks; e += stride) {
+        const int g = (int)(e / count);
+        dst[e] = ll_load(v.local + (size_t)g * v.cap + (e - (int64_t)g * count), v.seq);
+    }
+}
+
 // copy `count` doubles into the local exchange buffer; the last CTA to finish raises this rank's flag in every peer
 __global__ void __launch_bounds__(256) p2p_post_kernel(P2PView v, const double* __restrict__ src, int64_t count, unsigned int* ticket) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) v.data_local[i] = src[i];
@@ -111,6 +161,23 @@ __global__ void __launch_bounds__(256) p2p_small_allreduce_kernel(P2PView v, Sma
     }
 }
 
+__global__ void __launch_bounds__(256) ll_small_allreduce_kernel(LLView v, SmallMats sm) {
+    int64_t off = 0;
+    for (int q = 0; q < sm.n; ++q) {
+        const int cnt = sm.rows[q] * sm.cols[q];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x)
+            ll_push(v, off + e, sm.p[q][(e % sm.rows[q]) + (int64_t)(e / sm.rows[q]) * sm.ld[q]]);
+        off += cnt;
+    }
+    off = 0;
+    for (int q = 0; q < sm.n; ++q) {
+        const int cnt = sm.rows[q] * sm.cols[q];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x)
+            sm.p[q][(e % sm.rows[q]) + (int64_t)(e / sm.rows[q]) * sm.ld[q]] = ll_sum(v, off + e);
+        off += cnt;
+    }
+}
+
 struct Comm {
     struct UniqueId { char internal[128]; };
     int nranks = 1, rank = 0;
@@ -133,6 +200,10 @@ struct Comm {
     static constexpr int NCHAN = 2;
     unsigned long long seq[NCHAN] = {0, 0};
     unsigned int* ticket = nullptr;   // device counters for the post kernels, one per channel
+    // LL region (after the flag/parity regions): per channel [2 parity][P2P_MAX_RANKS senders][ll_cap] x 16 bytes
+    int64_t ll_cap = 0;
+    unsigned int ll_seq[NCHAN] = {0, 0};
+    static constexpr int64_t LL_MAX_CAP = 262144;   // 64 MB per channel at most
 
     static constexpr size_t FLAG_BYTES = (size_t)P2P_MAX_RANKS * P2P_FLAG_STRIDE * sizeof(unsigned long long);
 
@@ -173,12 +244,27 @@ struct Comm {
     void p2p_alloc(size_t data_bytes) {
         if (xbuf) return;
         xdata_bytes = (data_bytes + 255) / 256 * 256;
-        DLRA_CUDA(cudaMalloc(&xbuf, NCHAN * chan_bytes()));
-        DLRA_CUDA(cudaMemset(xbuf, 0, NCHAN * chan_bytes()));
+        ll_cap = std::min<int64_t>((int64_t)(xdata_bytes / 8), LL_MAX_CAP);
+        DLRA_CUDA(cudaMalloc(&xbuf, NCHAN * chan_bytes() + NCHAN * ll_chan_bytes()));
+        DLRA_CUDA(cudaMemset(xbuf, 0, NCHAN * chan_bytes() + NCHAN * ll_chan_bytes()));
         DLRA_CUDA(cudaMalloc(&ticket, NCHAN * sizeof(unsigned int)));
         DLRA_CUDA(cudaMemset(ticket, 0, NCHAN * sizeof(unsigned int)));
     }
     size_t chan_bytes() const { return FLAG_BYTES + 2 * xdata_bytes; }
+    size_t ll_chan_bytes() const { return (size_t)2 * P2P_MAX_RANKS * (size_t)ll_cap * 16; }
+    bool ll_fits(int64_t count) const { return p2p && ll_cap > 0 && count <= ll_cap && !ll_disabled(); }
+    static bool ll_disabled() { static const bool d = getenv("DLRA_NO_LL") != nullptr; return d; }
+    LLView next_ll(int chan) {
+        unsigned int sq = ++ll_seq[chan];
+        if (sq == 0) sq = ++ll_seq[chan];   // 0 is the "empty" flag value
+        const size_t par = (size_t)(sq & 1);
+        const size_t base = NCHAN * chan_bytes() + (size_t)chan * ll_chan_bytes() + par * (size_t)P2P_MAX_RANKS * (size_t)ll_cap * 16;
+        LLView v;
+        v.nranks = nranks; v.rank = rank; v.seq = sq; v.cap = ll_cap;
+        v.local = (uint4*)(xbuf + base);
+        for (int g = 0; g < P2P_MAX_RANKS; ++g) v.peer[g] = (uint4*)((xpeer[g] ? xpeer[g] : xbuf) + base);
+        return v;
+    }
     void p2p_export(void* handle64) {
         cudaIpcMemHandle_t hd;
         DLRA_CUDA(cudaIpcGetMemHandle(&hd, xbuf));
@@ -233,6 +319,12 @@ struct Comm {
         if (nranks <= 1 || sm.n <= 0) return;
         int64_t total = 0;
         for (int q = 0; q < sm.n; ++q) total += (int64_t)sm.rows[q] * sm.cols[q];
+        if (ll_fits(total) && total <= 16384) {
+            ll_small_allreduce_kernel<<<1, 256, 0, cx.stream>>>(next_ll(0), sm);
+            cx.launches++;
+            DLRA_CUDA(cudaGetLastError());
+            return;
+        }
         if (p2p && (size_t)total * 8 <= xdata_bytes && total <= 65536) {
             P2PView v = next_view(0);
             p2p_small_allreduce_kernel<<<1, 256, 0, cx.stream>>>(v, sm);
@@ -259,6 +351,14 @@ struct Comm {
     // in-place sum over ranks
     void allreduce_sum(double* buf, int64_t count, Ctx& cx) {
         if (nranks <= 1 || count <= 0) return;
+        if (ll_fits(count)) {
+            // every thread spins only for elements it pushed itself: no grid-wide dependency, any grid size is safe
+            const int blocks = (int)std::min<int64_t>(cdiv(count, 256), 2 * (int64_t)cx.num_sms);
+            ll_allreduce_kernel<<<blocks, 256, 0, cx.stream>>>(next_ll(0), buf, count);
+            cx.launches++;
+            DLRA_CUDA(cudaGetLastError());
+            return;
+        }
         if (p2p) {
             DLRA_REQUIRE((size_t)count * 8 <= xdata_bytes, "P2P exchange region too small for this message");
             P2PView v = next_view(0);

@@ -60,6 +60,13 @@ struct Ctx {
     int64_t launches = 0;
     int num_sms = 148;
     unsigned int* counters = nullptr;   // zero-initialised device counters for last-block-done reductions (self-resetting)
+    // main stream only: tall products n x p times p x q go through the TMA/DMMA streaming kernels when they fit (pass_tma.cuh)
+    bool (*tall_gemm)(void* eng, int64_t n, int p, int q, const double* A, int64_t lda, const double* B, int64_t ldb, bool transB,
+                      double* C, int64_t ldc, double alpha, double beta) = nullptr;
+    void* tall_eng = nullptr;
+    // DLRA_PHASES=1: phase marks from helpers that only see the launch context (main stream only)
+    void (*mark_fn)(void* eng, const char* name) = nullptr;
+    void mark(const char* name) const { if (mark_fn) mark_fn(tall_eng, name); }
 };
 
 // compile-time loop: f(std::integral_constant<int, I>) for I = B .. E-1 (indices are constant expressions in the

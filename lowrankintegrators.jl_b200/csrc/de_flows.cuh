@@ -169,6 +169,51 @@ __global__ void __launch_bounds__(128) hadamard_rows_kernel(int64_t rows, int p,
     out[i + (int64_t)c * ldo] += coef * s;
 }
 
+
+// Same contraction for p <= 32 with the row of P and all p outputs of a row held in registers: the p x p slab T[:, b, :] is
+// staged in shared memory once per b and read as warp-wide broadcasts (one LDS.128 per two FMAs), so the kernel runs close
+// to the DFMA rate instead of issuing one cached global load per FMA (10x on the Burgers flows, profiles/r02).
+__global__ void __launch_bounds__(64) hadamard_rows32_kernel(int64_t rows, int p, const double* __restrict__ P, int64_t ldp,
+                                                            const double* __restrict__ Q, int64_t ldq, const double* __restrict__ T,
+                                                            double* __restrict__ out, int64_t ldo, double coef) {
+    __shared__ __align__(16) double Ts[32][32];   // Ts[a][c] = T[a, b, c]
+    const int64_t i = (int64_t)blockIdx.x * 64 + threadIdx.x;
+    const bool ok = i < rows;
+    double pr[32], acc[32];
+#pragma unroll
+    for (int a = 0; a < 32; ++a) { pr[a] = (ok && a < p) ? P[i + (int64_t)a * ldp] : 0.0; acc[a] = 0.0; }
+    for (int b = 0; b < p; ++b) {
+        __syncthreads();
+        for (int e = threadIdx.x; e < 32 * 32; e += 64) {
+            const int a = e & 31, c = e >> 5;
+            Ts[a][c] = (a < p && c < p) ? T[a + (int64_t)p * (b + (int64_t)p * c)] : 0.0;
+        }
+        __syncthreads();
+        const double qb = ok ? Q[i + (int64_t)b * ldq] : 0.0;
+        double t2[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) t2[c] = 0.0;
+#pragma unroll
+        for (int a = 0; a < 32; ++a) {
+            const double pa = pr[a];
+            const double2* row = reinterpret_cast<const double2*>(&Ts[a][0]);
+#pragma unroll
+            for (int c2 = 0; c2 < 16; ++c2) {
+                const double2 tv = row[c2];
+                t2[2 * c2] = fma(pa, tv.x, t2[2 * c2]);
+                t2[2 * c2 + 1] = fma(pa, tv.y, t2[2 * c2 + 1]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] = fma(qb, t2[c], acc[c]);
+    }
+    if (ok) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+            if (c < p) out[i + (int64_t)c * ldo] += coef * acc[c];
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------
 // per-engine DE workspace
 // ------------------------------------------------------------------------------------------------------
@@ -473,8 +518,12 @@ struct SideFlow : FlowRhs {
             const double* P = X; const double* Qm = X;
             if (d1) { apply_op(cx, *d1, rows, r, X, rows, s1, rows, 1.0, 0.0); P = s1; }
             if (d2) { apply_op(cx, *d2, rows, r, X, rows, s2, rows, 1.0, 0.0); Qm = s2; }
-            dim3 grid((unsigned)cdiv(rows, 128), (unsigned)r);
-            hadamard_rows_kernel<<<grid, 128, 0, cx.stream>>>(rows, r, P, rows, Qm, rows, T, out, rows, c_had);
+            if (r <= 32 && rows >= 2048) {
+                hadamard_rows32_kernel<<<(unsigned)cdiv(rows, 64), 64, 0, cx.stream>>>(rows, r, P, rows, Qm, rows, T, out, rows, c_had);
+            } else {
+                dim3 grid((unsigned)cdiv(rows, 128), (unsigned)r);
+                hadamard_rows_kernel<<<grid, 128, 0, cx.stream>>>(rows, r, P, rows, Qm, rows, T, out, rows, c_had);
+            }
             cx.launches++;
             DLRA_CUDA(cudaGetLastError());
         }

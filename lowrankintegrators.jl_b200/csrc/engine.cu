@@ -9,6 +9,12 @@
 
 using namespace dlra;
 
+static void phase_mark_hook(void* eng, const char* name) { phase_mark((dlra_engine*)eng, name); }
+static bool tall_gemm_hook(void* eng, int64_t n, int p, int q, const double* A, int64_t lda, const double* B, int64_t ldb, bool transB,
+                           double* C, int64_t ldc, double alpha, double beta) {
+    return tall_gemm_tma((dlra_engine*)eng, n, p, q, A, lda, B, ldb, transB, C, ldc, alpha, beta);
+}
+
 static thread_local std::string g_create_error;
 
 #define DLRA_API_BEGIN(h)                                                     \
@@ -84,6 +90,9 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         }
         e->sub[0] = SubStepperCfg(); e->sub[1] = SubStepperCfg(); e->sub[2] = SubStepperCfg();
         e->phase_timing = getenv("DLRA_PHASES") != nullptr;
+        e->cx.tall_eng = e;
+        if (!getenv("DLRA_NO_TALL_GEMM")) e->cx.tall_gemm = tall_gemm_hook;
+        if (e->phase_timing) e->cx.mark_fn = phase_mark_hook;
         DLRA_CUDA(cudaStreamSynchronize(e->cx.stream));
     } catch (const CudaError& ex) {
         g_create_error = ex.what();
@@ -113,7 +122,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
         if (h->own_free[i]) cudaEventDestroy(h->own_free[i]);
         if (h->own_ready[i]) cudaEventDestroy(h->own_ready[i]);
     }
-    h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release(); h->isvd.release();
+    h->gws.release(); h->tws.release(); h->wtmp.release(); h->jws.release(); h->nscr.release(); h->mscr.release(); h->part.release(); h->isvd.release(); h->bstage.release();
     for (auto& pr : h->pass_events) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto& pm : h->phase_marks) cudaEventDestroy(pm.second);
     for (int i = 0; i < dlra_engine::NPROG; ++i) if (h->prog_ev[i]) cudaEventDestroy(h->prog_ev[i]);
@@ -1129,10 +1138,13 @@ extern "C" int dlra_stats(dlra_handle h, int64_t* kernel_launches, int64_t* pass
         if (reset == 0 || getenv("DLRA_PHASES_ALWAYS")) {
             int dev = 0; cudaGetDevice(&dev);
             double tot = 0; for (auto& a : acc) tot += a.second;
-            fprintf(stderr, "[dlra phases] device %d rank %d/%d: %d steps, %.1f us/step on the main stream:", dev, h->comm.rank, h->comm.nranks,
-                    steps, steps ? tot * 1e3 / steps : 0.0);
-            for (auto& a : acc) fprintf(stderr, " %s %.1f", a.first.c_str(), steps ? a.second * 1e3 / steps : 0.0);
-            fprintf(stderr, "\n");
+            char line[2048];
+            int off = snprintf(line, sizeof line, "[dlra phases] device %d rank %d/%d: %d steps, %.1f us/step on the main stream:", dev, h->comm.rank,
+                               h->comm.nranks, steps, steps ? tot * 1e3 / steps : 0.0);
+            for (auto& a : acc)
+                if (off < (int)sizeof line - 64) off += snprintf(line + off, sizeof line - off, " %s %.1f", a.first.c_str(), steps ? a.second * 1e3 / steps : 0.0);
+            snprintf(line + off, sizeof line - off, "\n");
+            fputs(line, stderr);   // one write per rank: lines of different ranks do not interleave
         }
         for (auto& pm : h->phase_marks) cudaEventDestroy(pm.second);
         h->phase_marks.clear();

@@ -88,6 +88,7 @@ struct dlra_engine {
     dlra::DevBuf gws, tws, wtmp, jws, nscr, mscr, part;  // grow-on-demand scratch
     dlra::DevBuf gws2, tws2, wtmp2;                       // scratch of the auxiliary stream
     dlra::DevBuf isvd;                                    // temporaries of dlra_truncated_svd
+    dlra::DevBuf bstage;                                  // staged small operand of tall_gemm_tma
 
     // data feed
     const double* prev = nullptr; int64_t ldprev = 0;

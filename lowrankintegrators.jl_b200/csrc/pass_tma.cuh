@@ -40,7 +40,8 @@ struct PassParams {
     int nsub;        // row sub-tiles per panel
     int npanels;
     int ntj;         // column tiles
-    double* K; int64_t ldk;       // K-use output (+=), may be null
+    double* K; int64_t ldk;       // K-use output (+=, or = when kstore), may be null
+    int kstore;
     double* Lpart; int64_t ldlp;  // [gridDim.x][ldlp x RT] per-CTA partial L (ldlp >= m), may be null
 };
 
@@ -312,7 +313,10 @@ pass_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CU
 #pragma unroll
                             for (int e = 0; e < 2; ++e) {
                                 const int c = coff + 8 * nb + 2 * k + e;
-                                if (c < prm.rc) prm.K[row + (int64_t)c * prm.ldk] += kacc[s][nb][e];
+                                if (c < prm.rc) {
+                                    double* dst = prm.K + row + (int64_t)c * prm.ldk;
+                                    *dst = prm.kstore ? kacc[s][nb][e] : *dst + kacc[s][nb][e];
+                                }
                             }
                     }
                 }
@@ -432,22 +436,31 @@ inline PassGrid pass_grid(dlra_engine* e, int csize) {
 // one launch: factor columns [0, rc) of Vf / Uf / K, RT per CTA, g.csize >= ceil(rc / RT) CTAs per cluster.
 // Lpart: g.ctas() partials of ldlp x RT doubles; the partials of the factor columns [RT*q, RT*q + RT) are those of the CTAs
 // with rank q in their cluster, i.e. blocks q, q + csize, q + 2*csize, ...
+// mcols > 0: the streamed matrix has mcols columns instead of e->m (a tall factor in the role of ΔA: tall_gemm below);
+// kstore: K = ΔA·Vf instead of K += ; timed = false keeps such launches out of the pass statistics
+struct PassOpts {
+    int64_t mcols = 0;
+    bool kstore = false;
+    bool timed = true;
+};
+
 template <int RT, bool DO_K, bool DO_L, bool DIFF>
 inline void launch_pass(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
-                        double* K, int64_t ldk, double* Lpart, int64_t ldlp, const PassGrid& g) {
+                        double* K, int64_t ldk, double* Lpart, int64_t ldlp, const PassGrid& g, const PassOpts& po = PassOpts()) {
+    const int64_t mm = po.mcols > 0 ? po.mcols : e->m;
     using SM = PassSmem<RT, DO_K, DO_L, DIFF>;
     static_assert(SM::NST >= 2, "pipeline needs at least two stages");
     auto kern = pass_kernel<RT, DO_K, DO_L, DIFF>;
-    CUtensorMap mapA = make_map_2d(d.A, e->n, e->m, d.lda, 16, PT_TJ, true);
-    CUtensorMap mapP = DIFF ? make_map_2d(d.Aprev, e->n, e->m, d.ldap, 16, PT_TJ, true) : mapA;
+    CUtensorMap mapA = make_map_2d(d.A, e->n, mm, d.lda, 16, PT_TJ, true);
+    CUtensorMap mapP = DIFF ? make_map_2d(d.Aprev, e->n, mm, d.ldap, 16, PT_TJ, true) : mapA;
     CUtensorMap mapU = DO_L ? make_map_2d(Uf, e->n, rc, ldu, 16, RT, true) : mapA;
-    CUtensorMap mapV = DO_K ? make_map_2d(Vf, e->m, rc, ldv, 16, RT, true) : mapA;
+    CUtensorMap mapV = DO_K ? make_map_2d(Vf, mm, rc, ldv, 16, RT, true) : mapA;
     PassParams prm;
-    prm.n = e->n; prm.m = e->m; prm.rc = rc; prm.nsub = g.nsub; prm.npanels = g.npanels; prm.ntj = (int)cdiv(e->m, PT_TJ);
-    prm.K = K; prm.ldk = ldk; prm.Lpart = Lpart; prm.ldlp = ldlp;
-    const double bytes = (double)e->n * (double)e->m * 8.0 * (DIFF ? 2.0 : 1.0);
-    const double flops = 2.0 * (double)e->n * (double)e->m * rc * ((DO_K ? 1 : 0) + (DO_L ? 1 : 0));
-    pass_timer_begin(e, bytes, (DO_K && DO_L) ? 0 : (DO_K ? 1 : 2), flops);
+    prm.n = e->n; prm.m = mm; prm.rc = rc; prm.nsub = g.nsub; prm.npanels = g.npanels; prm.ntj = (int)cdiv(mm, PT_TJ);
+    prm.K = K; prm.ldk = ldk; prm.Lpart = Lpart; prm.ldlp = ldlp; prm.kstore = po.kstore ? 1 : 0;
+    const double bytes = (double)e->n * (double)mm * 8.0 * (DIFF ? 2.0 : 1.0);
+    const double flops = 2.0 * (double)e->n * (double)mm * rc * ((DO_K ? 1 : 0) + (DO_L ? 1 : 0));
+    if (po.timed) pass_timer_begin(e, bytes, (DO_K && DO_L) ? 0 : (DO_K ? 1 : 2), flops);
     if (g.csize == 1) {
         kern<<<g.ctas(), PT_THREADS, SM::TOTAL, e->cx.stream>>>(mapA, mapP, mapU, mapV, prm);
     } else {
@@ -462,7 +475,7 @@ inline void launch_pass(dlra_engine* e, const Delta& d, int rc, const double* Vf
         cfg.attrs = at; cfg.numAttrs = 1;
         DLRA_CUDA(cudaLaunchKernelEx(&cfg, kern, mapA, mapP, mapU, mapV, prm));
     }
-    pass_timer_end(e);
+    if (po.timed) pass_timer_end(e);
     e->cx.launches++;
     DLRA_CUDA(cudaGetLastError());
 }
@@ -482,10 +495,10 @@ inline PassGrid pass_grid_rt(dlra_engine* e, bool dk, bool dl, bool df, int csiz
 }
 template <int RT>
 inline void launch_pass_rt(dlra_engine* e, const Delta& d, int rc, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
-                           double* K, int64_t ldk, double* Lpart, int64_t ldlp, const PassGrid& g) {
+                           double* K, int64_t ldk, double* Lpart, int64_t ldlp, const PassGrid& g, const PassOpts& po = PassOpts()) {
     const bool dk = K != nullptr, dl = Lpart != nullptr, df = d.Aprev != nullptr;
 #define DLRA_PASS_CASE(a, b, c) \
-    if (dk == a && dl == b && df == c) return launch_pass<RT, a, b, c>(e, d, rc, Vf, ldv, Uf, ldu, K, ldk, Lpart, ldlp, g);
+    if (dk == a && dl == b && df == c) return launch_pass<RT, a, b, c>(e, d, rc, Vf, ldv, Uf, ldu, K, ldk, Lpart, ldlp, g, po);
     DLRA_PASS_CASE(true, true, false)
     DLRA_PASS_CASE(true, true, true)
     DLRA_PASS_CASE(true, false, false)
@@ -499,11 +512,13 @@ inline void launch_pass_rt(dlra_engine* e, const Delta& d, int rc, const double*
 // row-sharded runs) and the initial term  L += Vi·Siᵀ  (the reference's `mul!(VS, V, S')` before the L-step,
 // unconventional.jl:145) in ONE launch.  XR: post the local sum to the exchange buffer, the last CTA raises this rank's
 // sequence flag in every peer, then all CTAs wait for the peers' flags and add the peers' slices in rank order.
-template <bool XR>
+// XR: 0 = single GPU, 1 = flag protocol (post + sequence flags), 2 = LL protocol (flag-in-data push, no fences: every thread
+// pushes the sums of its own elements into all ranks' buffers and collects the peers' copies of the same elements)
+template <int XR>
 __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int nparts, const double* __restrict__ part, int64_t ldlp,
                                                          int64_t part_stride, int rt, const double* __restrict__ Vi, int64_t ldvi,
                                                          const double* __restrict__ Si, int64_t ldsi, int rk, double* __restrict__ L,
-                                                         int64_t ldl, P2PView v, unsigned int* ticket, int s_in_smem) {
+                                                         int64_t ldl, P2PView v, unsigned int* ticket, int s_in_smem, LLView lv) {
     extern __shared__ double Ss[];   // [rc][rk] (when it fits the default dynamic shared memory; else S is read through the cache)
     if (Vi && s_in_smem) {
         for (int e = threadIdx.x; e < rc * rk; e += blockDim.x) Ss[e] = Si[(e / rk) + (int64_t)(e % rk) * ldsi];
@@ -531,10 +546,19 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
         const double* pp = part + (int64_t)(c / rt) * ldlp * rt + j + (int64_t)(c % rt) * ldlp;
 #pragma unroll 8
         for (int p = 0; p < nparts; ++p) s += pp[(int64_t)p * part_stride];
-        if (XR) v.data_local[e] = s;
+        if (XR == 2) ll_push(lv, e, s);
+        else if (XR == 1) v.data_local[e] = s;
         else L[j + (int64_t)c * ldl] = s + init_term(j, c);
     }
-    if (!XR) return;
+    if (XR == 0) return;
+    if (XR == 2) {
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gstride) {
+            const int64_t j = e % m;
+            const int c = (int)(e / m);
+            L[j + (int64_t)c * ldl] = ll_sum(lv, e) + init_term(j, c);
+        }
+        return;
+    }
     __syncthreads();
     __shared__ bool last;
     if (threadIdx.x == 0) {
@@ -574,12 +598,15 @@ inline void l_finalize(dlra_engine* e, int rc, int nparts, const double* part, i
     const int s_in_smem = (size_t)rc * rk * sizeof(double) <= 40 * 1024 ? 1 : 0;
     const size_t smem = (Vi && s_in_smem) ? (size_t)rc * rk * sizeof(double) : 0;
     if (cm.nranks <= 1) {
-        l_finalize_kernel<false><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, P2PView{}, nullptr, s_in_smem);
+        l_finalize_kernel<0><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, P2PView{}, nullptr, s_in_smem, LLView{});
+        cx.launches++;
+    } else if (cm.ll_fits(total)) {
+        l_finalize_kernel<2><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, P2PView{}, nullptr, s_in_smem, cm.next_ll(chan));
         cx.launches++;
     } else if (cm.p2p) {
         DLRA_REQUIRE((size_t)total * 8 <= cm.xdata_bytes, "P2P exchange region too small for an L chunk");
         P2PView v = cm.next_view(chan);
-        l_finalize_kernel<true><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, v, cm.ticket_of(chan), s_in_smem);
+        l_finalize_kernel<1><<<grid, 256, smem, cx.stream>>>(e->m, rc, nparts, part, ldlp, part_stride, rt, Vi, ldvi, Si, ldsi, rk, L, ldl, v, cm.ticket_of(chan), s_in_smem, LLView{});
         cx.launches++;
     } else {
         // NCCL transport: local reduction, library all-reduce of the dense chunk (ldl == m), then the initial term
@@ -611,7 +638,7 @@ inline int pass_fused_rt() { static int v = env_int("DLRA_FUSED_RT", 16, 16, 32)
 // Lout is COMPLETE on return: summed over this rank's panels, over the ranks of a row-sharded run, plus Vi·Siᵀ if given.
 inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf, int64_t ldv, const double* Uf, int64_t ldu,
                         double* K, int64_t ldk, double* Lout, int64_t ldl, const double* Vi = nullptr, int64_t ldvi = 0,
-                        const double* Si = nullptr, int64_t ldsi = 0) {
+                        const double* Si = nullptr, int64_t ldsi = 0, const PassOpts& po = PassOpts()) {
     // factor operands must satisfy the TMA alignment rules too; otherwise stage them through aligned scratch
     DLRA_REQUIRE((!K || tma_ok(Vf, ldv)) && (!Lout || tma_ok(Uf, ldu)), "factor buffers must be 16-byte aligned with even ld");
     const int64_t ldlp = round_up(e->m, 2);
@@ -631,13 +658,35 @@ inline void tma_pass_KL(dlra_engine* e, const Delta& d, int r, const double* Vf,
         else g = pass_grid_rt<32>(e, dk, dl, df, csize);
         if (dl) e->part.ensure((int64_t)g.ctas() * ldlp * rt, e->cx.stream);
         double* Lp = dl ? e->part.p : nullptr;
-        if (rt == 8) launch_pass_rt<8>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g);
-        else if (rt == 16) launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g);
-        else launch_pass_rt<32>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g);
+        if (rt == 8) launch_pass_rt<8>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g, po);
+        else if (rt == 16) launch_pass_rt<16>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g, po);
+        else launch_pass_rt<32>(e, d, rc, Vc, ldv, Uc, ldu, Kc, ldk, Lp, ldlp, g, po);
         // CTA q of every cluster holds the partial of the factor columns [rt*q, rt*q + rt)
         if (dl) l_finalize(e, rc, g.nclusters, Lp, ldlp, rt, csize, Vi, ldvi, Si ? Si + c0 : nullptr, ldsi, r, Lout + (int64_t)c0 * ldl, ldl);
         c0 += rc;
     }
+}
+
+// Tall product on the streaming machinery:  C (n x q) = beta*C + alpha * A (n x p) * op(B),  beta in {0, 1} — the tall factor A
+// plays the role of ΔA in a K-only sweep (TMA tiles, DMMA), op(B) is staged (scaled, transposed) into a dense p x q block.
+// Used for the O(n r^2) products of wide steps (U0*S0, the BCGS2 projections, Uhat*P), where the one-thread-per-row kernel
+// runs at a third of this speed.  Returns false when the shape or alignment does not fit (caller falls back).
+inline bool tall_gemm_tma(dlra_engine* e, int64_t n, int p, int q, const double* A, int64_t lda, const double* B, int64_t ldb, bool transB,
+                          double* C, int64_t ldc, double alpha, double beta) {
+    if (e->flags & DLRA_FORCE_GENERIC) return false;
+    // measured (profiles/r02): pays off for wide products only — thin ones (BCGS2 projections with q = 16, ranks <= 32) are
+    // faster on the one-thread-per-row kernel, whose launch has no pipeline to fill
+    if (n != e->n || n < 65536 || p < 48 || q < 32 || (p % 2) != 0 || (beta != 0.0 && beta != 1.0)) return false;
+    if (n >= ((int64_t)1 << 31) || (n % 2) != 0 || !tma_ok(A, lda)) return false;
+    Ctx& cx = e->cx;
+    e->bstage.ensure((int64_t)p * q, cx.stream);
+    copy_mat(cx, p, q, B, ldb, transB, e->bstage.p, p, alpha, 0.0);
+    Delta d;
+    d.A = A; d.lda = lda;
+    PassOpts po;
+    po.mcols = p; po.kstore = (beta == 0.0); po.timed = false;
+    tma_pass_KL(e, d, q, e->bstage.p, p, nullptr, 0, C, ldc, nullptr, 0, nullptr, 0, nullptr, 0, po);
+    return true;
 }
 
 // Sout (p x q) = Lfᵀ·(ΔA·Rf): the K-use streams W = ΔA·Rf (n x q, 8·n·q bytes — <1% of the ΔA traffic) and a

@@ -309,6 +309,224 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows,
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// CTA-wide Householder panel: the 8 warps of a CTA factor ONE 1024 x CP panel together (warp w holds rows 128 w .. 128 w + 127
+// in registers, the pivot rows live in warp 0).  Per column the warps' partial dot products meet in shared memory (one
+// __syncthreads, double-buffered), every warp forms the same reflector and updates its own rows.  Compared with the
+// two-level scheme above (8 independent 128-row panels, then one warp factoring the 8 stacked R's while 7 warps idle, then a
+// chain product) a 1024-row block costs ONE panel factorisation + ONE explicit-Q recurrence instead of two of each.
+// ------------------------------------------------------------------------------------------------------
+template <int CP, int RPL, int NW>
+__device__ __forceinline__ void cta_panel_qr(double (&a)[RPL][CP], double* vs, int vld, double* tau_s, int warp, int lane, double* bc,
+                                             double* part /*[2][NW][CP]*/, double* prow /*[2][CP]*/) {
+    constexpr int SH = (CP == 16) ? 1 : 2;
+#pragma unroll 1
+    for (int j0 = 0; j0 < CP; j0 += 2) {
+        static_for<0, 2>([&](auto PP) {
+            constexpr int P = decltype(PP)::value;
+            const int j = j0 + P;
+            const int par = j & 1;
+            double xm[RPL];
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) xm[q] = ((warp > 0) || (q > 0) || (lane > j)) ? a[q][P] : 0.0;
+            double e[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                double s = 0.0;
+                if (c + P < CP) {
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) s = fma(xm[q], a[q][c + P], s);
+                }
+                e[c] = s;
+            }
+            const double h = TReduce<CP, 16>::run(e, lane);
+            if ((lane & ((1 << SH) - 1)) == 0) part[(par * NW + warp) * CP + (lane >> SH)] = h;
+            if (warp == 0 && lane == j) {
+#pragma unroll
+                for (int c = P; c < CP; ++c) prow[par * CP + c] = a[0][c];
+            }
+            __syncthreads();
+            if (lane < CP) {   // every warp forms the same totals in the same order
+                double tsum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) tsum += part[(par * NW + w) * CP + lane];
+                bc[lane] = tsum;
+            }
+            __syncwarp();
+            const double alpha = prow[par * CP + P];
+            const double ss = bc[0];
+            double t = 0.0, scale = 0.0, beta = alpha;
+            if (ss > 0.0) {
+                const double nrm2 = fma(alpha, alpha, ss);
+                const double rn = rsqrt(nrm2);
+                beta = -copysign(nrm2 * rn, alpha);
+                t = fma(fabs(alpha), rn, 1.0);
+                scale = 1.0 / (alpha - beta);
+            }
+            if (warp == 0 && lane == 0) tau_s[j] = t;
+            double vm[RPL];
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) {
+                vm[q] = xm[q] * scale;
+                a[q][P] = ((warp > 0) || (q > 0) || (lane > j)) ? vm[q] : a[q][P];
+            }
+            if (warp == 0 && lane == j) { a[0][P] = beta; vm[0] = 1.0; }
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) vs[j * vld + lane + 32 * q] = a[q][P];
+#pragma unroll
+            for (int c = P + 1; c < CP; ++c) {
+                const double arow = prow[par * CP + c];
+                const double ec = bc[c - P];
+                const double w = (arow + ec * scale) * t;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) a[q][c] = fma(-w, vm[q], a[q][c]);
+            }
+            __syncwarp();
+        });
+#pragma unroll
+        for (int c = 2; c < CP; ++c)
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) a[q][c - 2] = a[q][c];
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) { a[q][CP - 2] = 0.0; a[q][CP - 1] = 0.0; }
+    }
+    __syncthreads();
+}
+
+template <int CP, int RPL, int NW>
+__device__ __forceinline__ void cta_panel_formq(double (&a)[RPL][CP], const double* vs, int vld, const double* tau_s, int warp, int lane,
+                                                double* bc, double* part) {
+    constexpr int SH = (CP == 16) ? 1 : 2;
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+        for (int q = 0; q < RPL; ++q) a[q][c] = 0.0;
+#pragma unroll 1
+    for (int j0 = CP - 2; j0 >= 0; j0 -= 2) {
+#pragma unroll
+        for (int c = CP - 1; c >= 2; --c)
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) a[q][c] = a[q][c - 2];
+        static_for<0, 2>([&](auto PP) {
+            constexpr int P = 1 - decltype(PP)::value;
+            const int j = j0 + P;
+            const int par = j & 1;
+            const double t = tau_s[j];
+            double vm[RPL];
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) vm[q] = ((warp > 0) || (q > 0) || (lane > j)) ? vs[j * vld + lane + 32 * q] : 0.0;
+            double e[CP];
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                double s = 0.0;
+                if (c + P + 1 < CP) {
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) s = fma(vm[q], a[q][c + P + 1], s);
+                }
+                e[c] = s;
+            }
+            const double h = TReduce<CP, 16>::run(e, lane);
+            if ((lane & ((1 << SH) - 1)) == 0) part[(par * NW + warp) * CP + (lane >> SH)] = h;
+            __syncthreads();
+            if (lane < CP) {
+                double tsum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) tsum += part[(par * NW + w) * CP + lane];
+                bc[lane] = tsum;
+            }
+            __syncwarp();
+            if (warp == 0 && lane == j) vm[0] = 1.0;
+#pragma unroll
+            for (int c = P + 1; c < CP; ++c) {
+                const double w = bc[c - P - 1] * t;
+#pragma unroll
+                for (int q = 0; q < RPL; ++q) a[q][c] = fma(-w, vm[q], a[q][c]);
+            }
+#pragma unroll
+            for (int q = 0; q < RPL; ++q) a[q][P] = -t * vm[q];
+            if (warp == 0 && lane == j) a[0][P] = 1.0 - t;
+            __syncwarp();
+        });
+    }
+}
+
+template <int CP>
+struct TsqrCtaSmem {
+    static constexpr int PROWS = 32 * TSQR_RPL0;
+    static constexpr size_t PARK = (size_t)CP * TSQR_NW * PROWS;        // Householder vectors of the 1024 x CP panel
+    static constexpr size_t MISC = (size_t)2 * TSQR_NW * CP + 2 * CP + CP + (size_t)TSQR_NW * 2 * CP + CP * CP;
+    static constexpr size_t BYTES = (PARK + MISC) * sizeof(double);
+};
+
+// one CTA: thin QR of rows [1024 b, 1024 b + 1024) of A -> explicit Q block (in place allowed) + its CP x CP R factor
+template <int CP>
+__global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_cta_kernel(int64_t rows, int C, const double* __restrict__ A, int64_t lda,
+                                                                  double* __restrict__ Q, int64_t ldq,
+                                                                  double* __restrict__ Rstack, int64_t ldr, TsqrAdd add) {
+    using SM = TsqrCtaSmem<CP>;
+    constexpr int RPL0 = TSQR_RPL0;
+    constexpr int PROWS = SM::PROWS;
+    constexpr int VLD = TSQR_NW * PROWS;
+    extern __shared__ __align__(16) double tsm[];
+    double* park = tsm;                                   // [CP][VLD]
+    double* part = park + SM::PARK;                       // [2][NW][CP]
+    double* prow = part + 2 * TSQR_NW * CP;               // [2][CP]
+    double* taus = prow + 2 * CP;                         // [CP]
+    double* bcast = taus + CP;                            // [NW][2*CP]
+    double* sadd = bcast + TSQR_NW * 2 * CP;              // [CP][CP] staged Sa of the fused rank-k update
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* bc = bcast + warp * 2 * CP;
+    const int64_t row0 = (int64_t)blockIdx.x * TSQR_BR + warp * PROWS;
+    double* mypark = park + warp * PROWS;
+    double a[RPL0][CP];
+    bool ok[RPL0];
+#pragma unroll
+    for (int q = 0; q < RPL0; ++q) ok[q] = (row0 + lane + 32 * q) < rows;
+    {
+        const double* col = A + row0 + lane;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+#pragma unroll
+            for (int q = 0; q < RPL0; ++q) a[q][c] = (ok[q] && c < C) ? col[32 * q] : 0.0;
+            col += lda;
+        }
+    }
+    if (add.U) {
+        for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) {
+            const int kk = e / CP, c = e % CP;
+            sadd[e] = (kk < add.k && c < C) ? add.S[kk + (int64_t)c * add.lds] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int kk = 0; kk < add.k; ++kk) {
+            double u[RPL0];
+#pragma unroll
+            for (int q = 0; q < RPL0; ++q) u[q] = ok[q] ? add.U[row0 + lane + 32 * q + (int64_t)kk * add.ldu] : 0.0;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                const double sv = sadd[kk * CP + c];
+#pragma unroll
+                for (int q = 0; q < RPL0; ++q) a[q][c] = fma(u[q], sv, a[q][c]);
+            }
+        }
+    }
+    cta_panel_qr<CP, RPL0, TSQR_NW>(a, mypark, VLD, taus, warp, lane, bc, part, prow);
+    if (warp == 0 && lane < CP) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) Rstack[(int64_t)blockIdx.x * CP + lane + (int64_t)c * ldr] = (lane <= c) ? park[c * VLD + lane] : 0.0;
+    }
+    cta_panel_formq<CP, RPL0, TSQR_NW>(a, mypark, VLD, taus, warp, lane, bc, part);
+    double* qcol = Q + row0 + lane;
+#pragma unroll
+    for (int c = 0; c < CP; ++c) {
+#pragma unroll
+        for (int q = 0; q < RPL0; ++q)
+            if (ok[q] && c < C) qcol[32 * q] = a[q][c];
+        qcol += ldq;
+    }
+}
+
 // rows <= 128: one warp factors the whole matrix (used for the top of the tree and for all-gathered R stacks)
 template <int CP>
 __global__ void __launch_bounds__(32, 1) tsqr_small_kernel(int rows, int C, const double* __restrict__ A, int64_t lda,
@@ -345,31 +563,40 @@ __global__ void __launch_bounds__(32, 1) tsqr_small_kernel(int rows, int C, cons
 // region, raise the flag in every peer, wait for the peers, read their R factors straight into the register panel
 // (rows g*CP.. of the stacked G*CP x CP matrix, over NVLink), factor it, and write the replicated R plus THIS rank's CP x CP
 // block of the explicit Q.  Every rank factors the same stack in the same order => bit-identical R on all ranks.
-template <int CP>
-__global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, const double* __restrict__ Rloc, double* __restrict__ Rout,
+template <int CP, bool LL>
+__global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, LLView lv, const double* __restrict__ Rloc, double* __restrict__ Rout,
                                                           double* __restrict__ Xout) {
     constexpr int RPL = 4;   // G*CP <= 128 rows
     __shared__ double vs[CP][32 * RPL];
     __shared__ double taus[CP];
     __shared__ double bc[2 * CP];
     const int lane = threadIdx.x;
-    for (int e = lane; e < CP * CP; e += 32) v.data_local[e] = Rloc[e];
-    __syncwarp();
-    __threadfence_system();
-    if (lane < v.nranks) st_release_sys(v.flags_peer[lane] + (size_t)v.rank * P2P_FLAG_STRIDE, v.seq);
-    if (lane < v.nranks) {
-        const unsigned long long* f = v.flags_local + (size_t)lane * P2P_FLAG_STRIDE;
-        while (ld_acquire_sys(f) < v.seq) { }
+    const int nranks = LL ? lv.nranks : v.nranks, rank = LL ? lv.rank : v.rank;
+    if (LL) {
+        for (int e = lane; e < CP * CP; e += 32) ll_push(lv, e, Rloc[e]);   // flag-in-data: R goes straight into every rank's buffer
+    } else {
+        for (int e = lane; e < CP * CP; e += 32) v.data_local[e] = Rloc[e];
+        __syncwarp();
+        __threadfence_system();
+        if (lane < nranks) st_release_sys(v.flags_peer[lane] + (size_t)rank * P2P_FLAG_STRIDE, v.seq);
+        if (lane < nranks) {
+            const unsigned long long* f = v.flags_local + (size_t)lane * P2P_FLAG_STRIDE;
+            while (ld_acquire_sys(f) < v.seq) { }
+        }
+        __syncwarp();
     }
-    __syncwarp();
-    const int rows = v.nranks * CP;
+    const int rows = nranks * CP;
     double a[RPL][CP];
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
         const int gr = lane + 32 * q;
         const int g = gr / CP, i = gr % CP;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) a[q][c] = (gr < rows) ? ld_relaxed_sys(v.data_peer[g < v.nranks ? g : 0] + i + c * CP) : 0.0;
+        for (int c = 0; c < CP; ++c) {
+            if (gr >= rows) a[q][c] = 0.0;
+            else if (LL) a[q][c] = ll_load(lv.local + (size_t)g * lv.cap + i + c * CP, lv.seq);
+            else a[q][c] = ld_relaxed_sys(v.data_peer[g] + i + c * CP);
+        }
     }
     reg_panel_qr<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane, bc);
     if (lane < CP) {
@@ -380,9 +607,9 @@ __global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, const doub
 #pragma unroll
     for (int q = 0; q < RPL; ++q) {
         const int gr = lane + 32 * q;
-        if (gr >= v.rank * CP && gr < (v.rank + 1) * CP) {
+        if (gr >= rank * CP && gr < (rank + 1) * CP) {
 #pragma unroll
-            for (int c = 0; c < CP; ++c) Xout[(gr - v.rank * CP) + c * CP] = a[q][c];
+            for (int c = 0; c < CP; ++c) Xout[(gr - rank * CP) + c * CP] = a[q][c];
         }
     }
 }
@@ -440,6 +667,19 @@ inline void tsqr_level(Ctx& cx, int CP, int64_t rows, int C, const double* A, in
         return;
     }
     const unsigned nb = (unsigned)cdiv(rows, TSQR_BR);
+    static const bool legacy = getenv("DLRA_TSQR_LEGACY") != nullptr;
+    if (!legacy) {
+        static unsigned long long attr_devs_c = 0;
+        if (first_use_on_this_device(attr_devs_c)) {
+            DLRA_CUDA(cudaFuncSetAttribute(tsqr_cta_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrCtaSmem<8>::BYTES));
+            DLRA_CUDA(cudaFuncSetAttribute(tsqr_cta_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrCtaSmem<16>::BYTES));
+        }
+        if (CP == 8) tsqr_cta_kernel<8><<<nb, TSQR_NW * 32, TsqrCtaSmem<8>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr, add);
+        else tsqr_cta_kernel<16><<<nb, TSQR_NW * 32, TsqrCtaSmem<16>::BYTES, cx.stream>>>(rows, C, A, lda, Q, ldq, Rstack, ldr, add);
+        cx.launches++;
+        DLRA_CUDA(cudaGetLastError());
+        return;
+    }
     static unsigned long long attr_devs = 0;
     if (first_use_on_this_device(attr_devs)) {
         DLRA_CUDA(cudaFuncSetAttribute(tsqr_reg_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrSmem<8>::BYTES));
@@ -483,17 +723,26 @@ inline void tsqr(Ctx& cx, Comm& comm, int64_t rows, int C, const double* A, int6
     double* tail = ws + tsqr_ws_size(rows, C, comm.nranks) - 1024 - (int64_t)(comm.nranks + 1) * CP * CP * 4;
     double* Rloc = tsqr_local(cx, rows, C, A, lda, Q, ldq, ws, add);
     const double* Rfin = Rloc;
+    if (comm.nranks > 1) cx.mark("tsqr_local");
     if (comm.nranks > 1 && comm.p2p) {
         DLRA_REQUIRE(comm.nranks * CP <= 128, "too many ranks for the single-warp cross-rank R reduction");
         DLRA_REQUIRE((size_t)CP * CP * 8 <= comm.xdata_bytes, "P2P exchange region too small for an R factor");
         double* Rg = tail;                 // CP x CP replicated R
         double* X = tail + CP * CP;        // this rank's block of the stacked Q
-        P2PView v = comm.next_view(0);
-        if (CP == 8) tsqr_xrank_kernel<8><<<1, 32, 0, cx.stream>>>(v, Rloc, Rg, X);
-        else tsqr_xrank_kernel<16><<<1, 32, 0, cx.stream>>>(v, Rloc, Rg, X);
+        if (comm.ll_fits((int64_t)CP * CP)) {
+            LLView lv = comm.next_ll(0);
+            if (CP == 8) tsqr_xrank_kernel<8, true><<<1, 32, 0, cx.stream>>>(P2PView{}, lv, Rloc, Rg, X);
+            else tsqr_xrank_kernel<16, true><<<1, 32, 0, cx.stream>>>(P2PView{}, lv, Rloc, Rg, X);
+        } else {
+            P2PView v = comm.next_view(0);
+            if (CP == 8) tsqr_xrank_kernel<8, false><<<1, 32, 0, cx.stream>>>(v, LLView{}, Rloc, Rg, X);
+            else tsqr_xrank_kernel<16, false><<<1, 32, 0, cx.stream>>>(v, LLView{}, Rloc, Rg, X);
+        }
         cx.launches++;
         DLRA_CUDA(cudaGetLastError());
+        cx.mark("tsqr_xrank");
         apply_blocks(cx, CP, rows, C, Q, ldq, (int64_t)1 << 62, X, CP, 0);
+        cx.mark("tsqr_xapply");
         Rfin = Rg;
     } else if (comm.nranks > 1) {
         const int G = comm.nranks;

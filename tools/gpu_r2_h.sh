@@ -1,0 +1,9 @@
+#!/bin/bash
+set -u
+out=gpurun_out/r2_h
+mkdir -p "$out"
+echo "== pytest -m gpu"; timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -8 | tee "$out/pytest_gpu.txt"
+echo "== perf r=16"; DLRA_PHASES=1 timeout 200 python tools/perf_pass.py 65536 4096 16 20 bug,ksl,rabug snapshot lookahead 2>&1 | tee "$out/perf16.txt"
+DLRA_TSQR_LEGACY=1 timeout 200 python tools/perf_pass.py 65536 4096 16 20 bug,rabug snapshot lookahead 2>&1 | tee -a "$out/perf16.txt"
+echo "== cfg5 shard"; DLRA_PHASES=1 timeout 300 python tools/run_configs.py cfg5 2>&1 | tail -4 | tee "$out/cfg5.txt"
+echo "== bench"; timeout 600 python bench.py --no-cfg5 2>&1 | tail -1 | cut -c1-1500 | tee "$out/bench.txt"
