@@ -133,55 +133,60 @@ def run_reference(args):
 # GPU arm
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """Samples SM clocks and throttle reasons DURING the timed region (NVML).  NVML queries from a polling thread perturb the
-    measured process (profiles/r02/multi_gpu_phases.txt: a 20 ms poll cost rank 0 ~95 us per 1.4 ms step), so the thread polls
-    at the recipe's 200 ms period and sample() adds one reading from the main thread right after the timed steps have been
-    enqueued, i.e. while the GPU is still executing them."""
+    """SM clocks and throttle reasons DURING the timed region, the way the profiling recipe does it: a separate
+    `nvidia-smi --query-gpu=... -lms 100` process started before the timed steps and stopped after them.  (An in-process NVML
+    polling thread perturbed the measured rank: ~95 us per 1.4 ms step on rank 0 at N = 2, profiles/r02/multi_gpu_phases.txt.)"""
+
+    FIELDS = "timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
-        import threading
-        self.sm, self.reasons, self.mx = [], set(), None
-        self._stop = threading.Event()
-        self._thr = None
+        import subprocess
+        self.proc = None
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
-            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self._thr = threading.Thread(target=self._run, daemon=True)
-            self._thr.start()
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
-            self.nv = None
+            self.proc = None
 
-    def sample(self):
-        nv = self.nv
-        if nv is None:
-            return
-        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
-        try:
-            self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-            try:
-                mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-            except Exception:
-                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-            for k, bit in names.items():
-                if mask & bit:
-                    self.reasons.add(k)
-        except Exception:
-            pass
-
-    def _run(self):
-        while not self._stop.wait(0.2):
-            self.sample()
+    def mark(self):
+        """Wall-clock mark: only samples between the first and the last mark count (the regions under load)."""
+        import datetime
+        self.marks = getattr(self, "marks", []) + [datetime.datetime.now()]
 
     def stop(self):
-        if self._thr is not None:
-            self._stop.set()
-            self._thr.join(timeout=2)
-        if not self.sm:
-            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": []}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        import datetime
+        import signal
+        try:
+            self.proc.send_signal(signal.SIGINT)
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in (out or "").splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f")
+                marks = getattr(self, "marks", [])
+                if len(marks) >= 2 and not (marks[0] <= ts <= marks[-1]):
+                    continue
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": mx, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "how": "nvidia-smi -lms 100 in a separate process; samples between the start of the device-timed steps and the end of the end-to-end steps"}
 
 
 def cfg5_strong(args, lri, torch, dist, world, rank, local_rank, dev):
@@ -283,6 +288,8 @@ def run_gpu(args):
         dist.init_process_group(backend="nccl", device_id=dev)
     n, m, r = N_ROWS, M_COLS, RANK
     K, W = args.steps, max(args.warmup, 3)
+    # started now so that it is polling steadily long before the timed region (process start-up takes ~100 ms)
+    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("DLRA_BENCH_NO_SAMPLER")) else None
 
     # ---- synthetic inputs (untimed): ring of 3 snapshots, SURVEY.md §8d recipe scaled by shard
     g = torch.Generator(device=dev)
@@ -331,19 +338,17 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local_rank) if (rank == 0 and not os.environ.get("DLRA_BENCH_NO_SAMPLER")) else None
+    if sampler:
+        sampler.mark()
     eng.event_record(0)
     t_host0 = time.perf_counter()
     for i in range(W, W + K):
         step(i)
     host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / K   # host time per step of the enqueue loop (throttled to <= 8 steps ahead)
     eng.event_record(1)
-    if sampler:
-        sampler.sample()   # the last timed steps are still running on the device
     ms_total = eng.event_elapsed_ms(0, 1)
     eng.sync()
     torch.cuda.synchronize()
-    clocks = sampler.stop() if sampler else None
     st = eng.stats()
     brk = eng.pass_breakdown()
     eng.set_profiling(False)
@@ -387,6 +392,9 @@ def run_gpu(args):
         t = torch.tensor([e2e_sec], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_sec = float(t.item())
+    if sampler:
+        sampler.mark()
+    clocks = sampler.stop() if sampler else None
     e2e = {"value": world / e2e_sec, "unit": UNIT, "h2d_bytes_per_step": n * m * 8, "d2h_bytes_per_step": (n * r + r * r + m * r) * 8,
            "steps": Ke, "note": "dlra_data_push_host (pinned host snapshot) + dlra_step_bug + dlra_get_factors_host per step"}
     eng.close()

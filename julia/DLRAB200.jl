@@ -282,4 +282,28 @@ function attach!(c::B200Cache, nranks::Integer, rank::Integer, allgather)
     check(c.h, ccall((:dlra_p2p_import, libdlra), Cint, (Handle, Cint, Cint, Ptr{UInt8}), c.h, nranks, rank, all))
 end
 
+# ---- asynchronous update_sol! (primitives.jl:82-90) and step progress -----------------------------------------------------------
+# `bufs = (U, S, V)` are host matrices the caller keeps alive (pinned with CUDA.Mem.pin for a truly asynchronous copy); they hold
+# the factors of the step after which this was called once `save_wait` has returned.  The step stream is not stalled.
+function save_factors_async!(c::B200Cache, U::Matrix{Float64}, S::Matrix{Float64}, V::Matrix{Float64})
+    r = Ref{Cint}(0)
+    check(c.h, ccall((:dlra_save_factors_async, libdlra), Cint,
+                     (Handle, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ref{Cint}),
+                     c.h, U, size(U, 1), S, size(S, 1), V, size(V, 1), r))
+    return Int(r[])
+end
+save_wait(c::B200Cache) = check(c.h, ccall((:dlra_save_wait, libdlra), Cint, (Handle,), c.h))
+
+# (steps enqueued, steps completed on the device); wait_for > completed blocks until that many steps are done
+function progress(c::B200Cache; wait_for::Integer = -1)
+    enq = Ref{Int64}(0); done = Ref{Int64}(0)
+    check(c.h, ccall((:dlra_progress, libdlra), Cint, (Handle, Ref{Int64}, Ref{Int64}, Int64), c.h, enq, done, wait_for))
+    return Int(enq[]), Int(done[])
+end
+
+# OrdinaryDiffEq's `maxiters` of the K/S/L sub-integrators (flow = FLOW_K | FLOW_S | FLOW_L); a step that hits it throws
+# DLRAError(7, ...) (DLRA_EMAXITERS, the reference's retcode MaxIters) and leaves integrator.u untouched
+set_maxiters!(c::B200Cache, flow::Integer, maxiters::Integer) =
+    check(c.h, ccall((:dlra_set_substepper_maxiters, libdlra), Cint, (Handle, Cint, Int64), c.h, flow, maxiters))
+
 end # module

@@ -314,6 +314,10 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     if adaptive:
         rmax = int(min(alg.rmax, 128, m // 2 if m >= 2 else 1))
         rmax = max(rmax, r0)
+        if alg.rmax < 2 ** 62 and rmax < alg.rmax:   # an explicit r_max the engine cannot honour (workspaces are sized once for 2*rmax <= 256 columns)
+            import warnings
+            warnings.warn(f"RankAdaptiveUnconventionalAlgorithm: rmax = {alg.rmax} clamped to {rmax} "
+                          f"(libdlra.so supports augmented bases of up to 256 columns and 2*rmax <= m)")
     eng = (Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic, aug_basis_first=True)
            if aug_basis_first else Engine(n, m, r0, rmax, rank_adaptive=adaptive, device=device, force_generic=force_generic))
     if comm == "torch":  # torch.distributed only hands out the IPC handles / the ncclUniqueId
@@ -349,6 +353,15 @@ def init(prob, alg, dt, *, device=None, comm=None, save_everystep=True, force_ge
     return integ
 
 
+def _push_current(integ, eng, y, t, dt):
+    """update_data! for the step at time t unless a previous BUG step with lookahead already handed y(t + dt) to the engine
+    (step(integ, other_alg) after a lookahead step must not push the same snapshot twice)."""
+    if integ._pushed > 0:
+        integ._pushed -= 1
+        return
+    eng.data_push(_fetch(y, t, dt))
+
+
 def step(integ: DLRIntegrator, alg=None, dt=None):
     """step!(integrator, alg, dt): projector_splitting.jl:191-211, unconventional.jl:159-164,
     rank_adaptive_unconventional.jl:171-180, greedy_integrator.jl:106-111."""
@@ -368,7 +381,7 @@ def step(integ: DLRIntegrator, alg=None, dt=None):
                 eng.step_ksl(L.KSL_STRANG, t, dt)
         else:
             if is_data:
-                eng.data_push(_fetch(y, t, dt))
+                _push_current(integ, eng, y, t, dt)
             eng.step_ksl(L.KSL_PRIMAL if isinstance(alg.order, PrimalLieTrotter) else L.KSL_DUAL, t, dt)
     elif isinstance(alg, UnconventionalAlgorithm):
         if is_data:
@@ -384,12 +397,12 @@ def step(integ: DLRIntegrator, alg=None, dt=None):
         eng.step_bug(t, dt)
     elif isinstance(alg, RankAdaptiveUnconventionalAlgorithm):
         if is_data:
-            eng.data_push(_fetch(y, t, dt))
+            _push_current(integ, eng, y, t, dt)
         r_new, changed = eng.step_rabug(alg.tol, alg.rmax, t, dt)
         if changed:
             print(f"rank adjusted: new rank = {r_new}")  # rank_adaptive_unconventional.jl:230
     elif isinstance(alg, GreedyIntegrator):  # greedy_step! dispatches on (typeof(u), probType), greedy_integrator.jl:72-104
-        eng.data_push(_fetch(integ.prob.y, t, dt))
+        _push_current(integ, eng, integ.prob.y, t, dt)
         if integ.probType is MatrixHybridProblem:
             eng.step_greedy_two_factor(L.GREEDY_HYBRID, t, dt, alg.fsal_carry)
         elif integ.two_factor:

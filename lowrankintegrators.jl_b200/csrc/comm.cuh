@@ -63,6 +63,13 @@ __device__ __forceinline__ double ll_load(const uint4* p, unsigned int seq) {
     } while (f1 != seq || f2 != seq);
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
+// one attempt (no spinning): many of these can be in flight before the first flag is inspected
+__device__ __forceinline__ bool ll_try_load(const uint4* p, unsigned int seq, double& out) {
+    unsigned int lo, f1, hi, f2;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+    out = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+    return f1 == seq && f2 == seq;
+}
 // element e of this rank's contribution -> every rank's buffer
 __device__ __forceinline__ void ll_push(const LLView& v, int64_t e, double val) {
     for (int g = 0; g < v.nranks; ++g) ll_store(v.peer[g] + (size_t)v.rank * v.cap + e, val, v.seq);

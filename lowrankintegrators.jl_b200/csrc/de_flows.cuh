@@ -647,8 +647,7 @@ struct CoreFlow : FlowRhs {
             // Y1[a', (b,d)] = Σ_a S[a',a] TV[a,(b,d)]            (p x q^2)
             small_gemm(cx, p, q * q, q, S, p, false, TV, q, false, Y1, p, 1.0, 0.0);
             // Y2[(a'), b', d] = Σ_b S[b',b] Y1[a', b, d]: for each d: Y2_d (p x p) = Y1_d (p x q) · Sᵀ (q x p)
-            for (int d = 0; d < q; ++d)
-                small_gemm(cx, p, p, q, Y1 + (int64_t)d * p * q, p, false, S, p, true, Y2 + (int64_t)d * p * p, p, 1.0, 0.0);
+            small_gemm(cx, p, p, q, Y1, p, false, S, p, true, Y2, p, 1.0, 0.0, q, (int64_t)p * q, 0, (int64_t)p * p);   // one batched launch
             // out[c,d] += sign·c_had · Σ_{a',b'} TU[(a',b'), c] · Y2[(a',b'), d]     (TUᵀ·Y2 with p^2 rows)
             small_gemm(cx, p, q, p * p, TU, p * p, true, Y2, p * p, false, out, p, sign * c_had, 1.0);
         }

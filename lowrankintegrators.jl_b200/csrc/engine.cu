@@ -518,8 +518,11 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     const bool pre = sc.is_data && h->kl_ready && h->kl_rank == r;   // formed by the previous step's pipelined pass
     h->kl_ready = false;
     phase_mark(h, "step");
-    // the whole L-side chain (incl. the cross-rank sum of L on exchange channel 1) runs beside the K-side chain
-    const bool lfin_aux = pre && (h->comm.nranks <= 1 || h->comm.p2p) && !getenv("DLRA_LFIN_MAIN");
+    // Single GPU: the whole L-side chain runs beside the K-side chain.  Row-sharded runs keep the cross-rank sum of L on the main
+    // stream: measured at N = 2 (profiles/r02/multi_gpu_phases.txt) the spinning exchange kernel on the auxiliary stream competes
+    // with the K-side TSQR for SMs and sets up a ~120 us ping-pong of arrival skew between the ranks (DLRA_LFIN_AUX=1 re-enables it).
+    static const bool lfin_aux_multi = getenv("DLRA_LFIN_AUX") != nullptr;
+    const bool lfin_aux = pre && (h->comm.nranks <= 1 || (h->comm.p2p && lfin_aux_multi));
     if (pre) {
         // K = ΔA*V0 (already in UB) + U0*S0: the update is folded into the TSQR panel load below
         if (!lfin_aux)

@@ -398,7 +398,9 @@ inline void gemm_tn(Ctx& cx, int64_t n, int p, int q, const double* A, int64_t l
 // sides of the DE flows launch hundreds of these per step.
 __global__ void __launch_bounds__(256) small_gemm_kernel(int p, int q, int k, const double* __restrict__ A, int lda, int tA,
                                                          const double* __restrict__ B, int ldb, int tB, double* __restrict__ C, int ldc,
-                                                         double alpha, double beta) {
+                                                         double alpha, double beta, int64_t sA = 0, int64_t sB = 0, int64_t sC = 0) {
+    // strided batch along blockIdx.z (all strides 0 for a single product)
+    A += (int64_t)blockIdx.z * sA; B += (int64_t)blockIdx.z * sB; C += (int64_t)blockIdx.z * sC;
     __shared__ double As[32][33];   // As[l][i] = op(A)[i0 + i][l0 + l]
     __shared__ double Bs[32][33];   // Bs[l][j] = op(B)[l0 + l][j0 + j]
     const int i0 = blockIdx.x * 32, j0 = blockIdx.y * 32;
@@ -439,11 +441,12 @@ __global__ void __launch_bounds__(256) small_gemm_kernel(int p, int q, int k, co
         }
     }
 }
+// `batch` independent products with operand strides sA, sB, sC (doubles) in ONE launch
 inline void small_gemm(Ctx& cx, int p, int q, int k, const double* A, int lda, bool tA, const double* B, int ldb, bool tB,
-                       double* C, int ldc, double alpha, double beta) {
-    if (p <= 0 || q <= 0) return;
-    dim3 grid((unsigned)cdiv(p, 32), (unsigned)cdiv(q, 32));
-    small_gemm_kernel<<<grid, 256, 0, cx.stream>>>(p, q, k, A, lda, tA ? 1 : 0, B, ldb, tB ? 1 : 0, C, ldc, alpha, beta);
+                       double* C, int ldc, double alpha, double beta, int batch = 1, int64_t sA = 0, int64_t sB = 0, int64_t sC = 0) {
+    if (p <= 0 || q <= 0 || batch <= 0) return;
+    dim3 grid((unsigned)cdiv(p, 32), (unsigned)cdiv(q, 32), (unsigned)batch);
+    small_gemm_kernel<<<grid, 256, 0, cx.stream>>>(p, q, k, A, lda, tA ? 1 : 0, B, ldb, tB ? 1 : 0, C, ldc, alpha, beta, sA, sB, sC);
     cx.launches++;
     DLRA_CUDA(cudaGetLastError());
 }

@@ -591,11 +591,20 @@ __global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, LLView lv,
     for (int q = 0; q < RPL; ++q) {
         const int gr = lane + 32 * q;
         const int g = gr / CP, i = gr % CP;
+        if (LL) {
+            // all CP loads of a row are issued before the first flag is looked at (one L2 round trip per attempt, not CP)
+            bool ok;
+            do {
+                ok = true;
 #pragma unroll
-        for (int c = 0; c < CP; ++c) {
-            if (gr >= rows) a[q][c] = 0.0;
-            else if (LL) a[q][c] = ll_load(lv.local + (size_t)g * lv.cap + i + c * CP, lv.seq);
-            else a[q][c] = ld_relaxed_sys(v.data_peer[g] + i + c * CP);
+                for (int c = 0; c < CP; ++c) {
+                    if (gr >= rows) a[q][c] = 0.0;
+                    else ok &= ll_try_load(lv.local + (size_t)g * lv.cap + i + c * CP, lv.seq, a[q][c]);
+                }
+            } while (!ok);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CP; ++c) a[q][c] = (gr < rows) ? ld_relaxed_sys(v.data_peer[g] + i + c * CP) : 0.0;
         }
     }
     reg_panel_qr<CP, RPL>(a, &vs[0][0], 32 * RPL, taus, lane, bc);

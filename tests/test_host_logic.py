@@ -187,3 +187,17 @@ def test_driver_time_grid_matches_the_oracle_restatement(fake, tf, dt):
     steps = [c for c in fake.log[0].calls if c[0] == "ksl"]
     assert len(steps) == len(osol.Y) - 1
     assert np.allclose([c[2] for c in steps], [dt * k for k in range(len(steps))], atol=1e-12)      # t passed to every step
+
+
+def test_switching_algorithms_after_a_lookahead_step_pushes_each_snapshot_once(fake):
+    # the BUG lookahead leaves y(t + 2dt)... y(t + dt) of the NEXT step already queued in the engine; a following
+    # step with another algorithm must consume it instead of pushing the same snapshot again
+    y = _snaps(6)
+    integ = lri.init(lri.MatrixDataProblem(y, _u0()), lri.UnconventionalAlgorithm(), 1)
+    lri.step(integ)                                                     # pushes y[2], y[3] (lookahead), consumes y[2]
+    lri.step(integ, lri.ProjectorSplitting(lri.PrimalLieTrotter()))     # y[3] is already there
+    lri.step(integ, lri.RankAdaptiveUnconventionalAlgorithm(1e-3, rmax=2))
+    pushes = [c[1] for c in fake.log[0].calls if c[0] == "push"]
+    assert pushes == [1.0, 2.0, 3.0]
+    kinds = [c[0] for c in fake.log[0].calls if c[0] in ("bug", "ksl", "rabug")]
+    assert kinds == ["bug", "ksl", "rabug"]

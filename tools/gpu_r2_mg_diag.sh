@@ -6,11 +6,12 @@ mkdir -p "$out"
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus $N"
 for mode in ${MODES:-p2p_aux p2p_main nccl}; do
   case $mode in
-    p2p_aux) envs="";;
-    p2p_main) envs="DLRA_LFIN_MAIN=1";;
+    p2p_aux) envs="DLRA_LFIN_AUX=1";;
+    p2p_main) envs="";;
     nccl) envs="DLRA_COMM=nccl";;
     nccl_nosampler) envs="DLRA_COMM=nccl DLRA_BENCH_NO_SAMPLER=1";;
     p2p_nosampler) envs="DLRA_BENCH_NO_SAMPLER=1";;
+    p2p_noll) envs="DLRA_NO_LL=1";;
   esac
   echo "== $mode"
   env $envs DLRA_PHASES=1 timeout 600 $RUN --steps 50 --warmup 5 --no-cfg5 > "$out/bench_$mode.json" 2> "$out/bench_$mode.err"
