@@ -185,6 +185,36 @@ __global__ void __launch_bounds__(256) ll_small_allreduce_kernel(LLView v, Small
     }
 }
 
+// Row-sharded BUG tail in ONE single-CTA launch (r <= 16): all-reduce of M = U1ᵀU0 and of the core increment R = U1ᵀΔA·V1 (LL push /
+// collect, rank order) followed by the core update  S <- M·S·Nᵀ + R  (unconventional.jl:154-155) on the reduced values.
+__global__ void __launch_bounds__(256) ll_allreduce_core_kernel(LLView v, int r, double* __restrict__ M, double* __restrict__ R, int ld,
+                                                               double* __restrict__ S, const double* __restrict__ Nm) {
+    __shared__ double Ms[256], Rs[256], Ts[256], Ss[256];
+    const int i = threadIdx.x % 16, j = threadIdx.x / 16;
+    const bool in = i < r && j < r;
+    if (in) {
+        ll_push(v, threadIdx.x, M[i + (int64_t)j * ld]);
+        ll_push(v, 256 + threadIdx.x, R[i + (int64_t)j * ld]);
+    }
+    const double ms = in ? ll_sum(v, threadIdx.x) : 0.0;
+    const double rs = in ? ll_sum(v, 256 + threadIdx.x) : 0.0;
+    if (in) { M[i + (int64_t)j * ld] = ms; R[i + (int64_t)j * ld] = rs; }
+    Ms[threadIdx.x] = ms; Rs[threadIdx.x] = rs;
+    Ss[threadIdx.x] = in ? S[i + (int64_t)j * ld] : 0.0;
+    __syncthreads();
+    {
+        double t = 0.0;
+        for (int l = 0; l < r; ++l) t = fma(Ms[i + 16 * l], Ss[l + 16 * j], t);
+        Ts[threadIdx.x] = t;
+    }
+    __syncthreads();
+    if (in) {
+        double t = 0.0;
+        for (int l = 0; l < r; ++l) t = fma(Ts[i + 16 * l], Nm[j + (int64_t)l * ld], t);
+        S[i + (int64_t)j * ld] = t + Rs[threadIdx.x];
+    }
+}
+
 struct Comm {
     struct UniqueId { char internal[128]; };
     int nranks = 1, rank = 0;

@@ -151,6 +151,76 @@ __global__ void __launch_bounds__(256) tensor3_part_kernel(int64_t rows, int p, 
     }
 }
 
+
+// The same third-order tensor on the fp64 tensor pipe:  T[(a,b), c] = Σ_i Z[i,(a,b)]·W[i,c]  with  Z[i,(a,b)] = P[i,a]·Q[i,b]  formed in
+// registers — a (p² x rows)·(rows x p) product.  A CTA owns 128 (a,b) pairs (16 per warp: two 8-row DMMA blocks) x all c and a chunk of rows;
+// 32-row tiles of P, Q, W are staged row-major with a stride of 68 doubles (conflict-free fragment loads).  20x the scalar kernel above at
+// p = 32 (profiles/r02): that kernel spends three shared-memory loads per multiply-add.
+constexpr int T3_LD = 68, T3_ROWS = 32;
+constexpr int T3_SMEM_BYTES = 3 * T3_ROWS * T3_LD * (int)sizeof(double);
+template <int NB>   // NB = ceil(p / 8) column blocks of c (4 for p <= 32, 8 for p <= 64)
+__global__ void __launch_bounds__(256) tensor3_dmma_kernel(int64_t rows, int p, int64_t chunk_rows, const double* __restrict__ P, int64_t ldp,
+                                                          const double* __restrict__ Q, int64_t ldq, const double* __restrict__ Wm,
+                                                          int64_t ldw, double* __restrict__ Tpart) {
+    extern __shared__ __align__(16) double t3s[];
+    double* Ps = t3s; double* Qs = Ps + T3_ROWS * T3_LD; double* Ws = Qs + T3_ROWS * T3_LD;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k = lane & 3;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk_rows, r1 = min(rows, r0 + chunk_rows);
+    const int p2 = p * p;
+    const int mbase = blockIdx.y * 128 + warp * 16;
+    int ia[2], ib[2]; bool mok[2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+        const int m = mbase + 8 * mb + g;
+        mok[mb] = m < p2;
+        ia[mb] = mok[mb] ? m % p : 0;
+        ib[mb] = mok[mb] ? m / p : 0;
+    }
+    double acc[2][NB][2];
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
+    for (int64_t rr = r0; rr < r1; rr += T3_ROWS) {
+        __syncthreads();
+        // stage [32 rows][p (+ zero padding up to 8·NB)] of the three operands: global reads run along the rows of a column
+        for (int e = threadIdx.x; e < 8 * NB * T3_ROWS; e += 256) {
+            const int c = e / T3_ROWS, i = e % T3_ROWS;
+            const bool ok = (rr + i < r1) && (c < p);
+            Ps[i * T3_LD + c] = ok ? P[rr + i + (int64_t)c * ldp] : 0.0;
+            Qs[i * T3_LD + c] = ok ? Q[rr + i + (int64_t)c * ldq] : 0.0;
+            Ws[i * T3_LD + c] = ok ? Wm[rr + i + (int64_t)c * ldw] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int ks = 0; ks < T3_ROWS / 4; ++ks) {
+            const int row = (4 * ks + k) * T3_LD;
+            double af[2], bf[NB];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) af[mb] = mok[mb] ? Ps[row + ia[mb]] * Qs[row + ib[mb]] : 0.0;
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb) bf[nb] = Ws[row + 8 * nb + g];
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+        }
+    }
+    double* out = Tpart + (int64_t)blockIdx.x * p2 * p;
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb) {
+        const int m = mbase + 8 * mb + g;
+        if (m >= p2) continue;
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int c = 8 * nb + 2 * k + e;
+                if (c < p) out[m + (int64_t)p2 * c] = acc[mb][nb][e];
+            }
+    }
+}
+
 // out[i, c] (+)= coef * Σ_{a,b} P[i,a] Q[i,b] T[a + p*(b + p*c)]      (rows x p operands, p outputs per row)
 __global__ void __launch_bounds__(128) hadamard_rows_kernel(int64_t rows, int p, const double* __restrict__ P, int64_t ldp,
                                                            const double* __restrict__ Q, int64_t ldq, const double* __restrict__ T,
@@ -316,13 +386,31 @@ inline void tensor3(dlra_engine* e, DeWork* w, int64_t rows, int p, const double
     Ctx& cx = e->cx;
     DLRA_REQUIRE(p <= 64, "the Hadamard (column-wise nonlinear) term supports factor widths up to 64");
     const int64_t p3 = (int64_t)p * p * p;
-    const int slabs = (int)cdiv(p3, 4096);
-    int64_t want_chunks = std::max<int64_t>(1, (2 * cx.num_sms) / slabs);
-    int64_t chunk_rows = round_up(cdiv(rows, want_chunks), 32);
-    const int64_t nch = cdiv(rows, chunk_rows);
-    w->tpart.ensure(nch * p3, cx.stream);
-    dim3 grid((unsigned)nch, (unsigned)slabs);
-    tensor3_part_kernel<<<grid, 256, (size_t)3 * p * 32 * sizeof(double), cx.stream>>>(rows, p, chunk_rows, P, ldp, Q, ldq, Wm, ldw, w->tpart.p);
+    static const bool legacy = getenv("DLRA_TENSOR3_LEGACY") != nullptr;
+    int64_t nch;
+    if (!legacy) {
+        const int slabs = (int)cdiv((int64_t)p * p, 128);
+        const int64_t want_chunks = std::max<int64_t>(1, (2 * cx.num_sms) / slabs);
+        const int64_t chunk_rows = round_up(cdiv(rows, want_chunks), T3_ROWS);
+        nch = cdiv(rows, chunk_rows);
+        w->tpart.ensure(nch * p3, cx.stream);
+        static unsigned long long attr_devs = 0;
+        if (first_use_on_this_device(attr_devs)) {
+            DLRA_CUDA(cudaFuncSetAttribute(tensor3_dmma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+            DLRA_CUDA(cudaFuncSetAttribute(tensor3_dmma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
+        }
+        dim3 grid((unsigned)nch, (unsigned)slabs);
+        if (p <= 32) tensor3_dmma_kernel<4><<<grid, 256, T3_SMEM_BYTES, cx.stream>>>(rows, p, chunk_rows, P, ldp, Q, ldq, Wm, ldw, w->tpart.p);
+        else tensor3_dmma_kernel<8><<<grid, 256, T3_SMEM_BYTES, cx.stream>>>(rows, p, chunk_rows, P, ldp, Q, ldq, Wm, ldw, w->tpart.p);
+    } else {
+        const int slabs = (int)cdiv(p3, 4096);
+        int64_t want_chunks = std::max<int64_t>(1, (2 * cx.num_sms) / slabs);
+        int64_t chunk_rows = round_up(cdiv(rows, want_chunks), 32);
+        nch = cdiv(rows, chunk_rows);
+        w->tpart.ensure(nch * p3, cx.stream);
+        dim3 grid((unsigned)nch, (unsigned)slabs);
+        tensor3_part_kernel<<<grid, 256, (size_t)3 * p * 32 * sizeof(double), cx.stream>>>(rows, p, chunk_rows, P, ldp, Q, ldq, Wm, ldw, w->tpart.p);
+    }
     cx.launches++;
     DLRA_CUDA(cudaGetLastError());
     // view the p^3 entries as a (p^2) x p matrix for the generic fixed-order reduction

@@ -546,6 +546,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     if (pre) qr_nside_plus(h, K, r, h->U, h->S, r);       // ... overlaps U1 = qr(ΔA*V0 + U0*S0).Q
     else qr_nside(h, K, r, nullptr);                      //              U1 = qr(K).Q
     phase_mark(h, "qr_K");
+    // M must be formed BEFORE the pipelined pass: that pass writes the next step's K into the buffer of U0
     gram_nside_local(h, r, r, K, h->U, h->M);             // M = U1'*U0 (local rows; summed over ranks below)
     phase_mark(h, "gram_M");
     join_aux(h);
@@ -567,6 +568,22 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
             h->gws.ensure(gemm_tn_ws(cx, n, r, r), cx.stream);
             gemm_tn(cx, n, r, r, K, n, nullptr, 0, h->nscr.p, n, h->Rm, W, 1.0, 0.0, h->gws.p);   // Rm = U1'*W (local rows)
             h->kl_ready = true; h->kl_nparts = nparts; h->kl_ldlp = ldlp; h->kl_rank = r;
+            phase_mark(h, "pass_S(+KL_next)+gram");
+            if (h->comm.nranks > 1 && r <= 16 && h->comm.ll_fits(512)) {
+                // all-reduce of M and the core increment + core update in one single-CTA launch
+                ll_allreduce_core_kernel<<<1, 256, 0, cx.stream>>>(h->comm.next_ll(0), r, h->M, h->Rm, (int)W, h->S, h->N);
+                cx.launches++;
+                DLRA_CUDA(cudaGetLastError());
+                phase_mark(h, "allreduce_M_S");
+            } else {
+                allreduce_pair(h, h->M, r, r, h->Rm, r, r);
+                phase_mark(h, "allreduce_M_S");
+                core_update(cx, r, r, r, h->M, h->S, h->N, h->Rm, h->S, (int)W, h->T1);
+            }
+            phase_mark(h, "core_update");
+            std::swap(h->U, h->UB);
+            std::swap(h->V, h->VB);
+            return;
         } else {
             pass_S(h, sc.d, r, r, K, n, L, m, h->Rm, W);        // Rm = U1'*ΔA*V1 (local rows)
         }
@@ -669,6 +686,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     DLRA_REQUIRE(r2 <= m, "augmented basis wider than the matrix");
     int rcap = (int)std::min<int64_t>(rcap64, (int64_t)h->rmax);
     rcap = std::min(rcap, r2);
+    phase_mark(h, "step");
     double *Kh = h->UB, *Lh = h->VB;   // [K U0] -> Uhat ; [L V0] -> Vhat
     // DLRA_AUG_BASIS_FIRST: [U0 K], [V0 L] — same span; the leading (orthonormal) panel then skips its factorisation
     const bool first = (h->flags & DLRA_AUG_BASIS_FIRST) != 0;
@@ -686,12 +704,15 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     }
     copy_mat(cx, n, r, h->U, n, false, Uc, n);             // Uhat[:, r+1:end] = U0 (reference order) | Uhat[:, 1:r] = U0
     copy_mat(cx, m, r, h->V, m, false, Vc, m);
+    phase_mark(h, "KL_flows");
     fork_aux(h);
     qr_mside(h, aux_side(h), Lh, r2, nullptr, first ? r : 0);
     gram_mside(h, aux_side(h), r2, r, Lh, h->V, h->N);                   // N = Vhat'*V0
     qr_nside(h, Kh, r2, nullptr, first ? r : 0);
     gram_nside_local(h, r2, r, Kh, h->U, h->M);                          // M = Uhat'*U0 (2r x r), local rows
+    phase_mark(h, "qr_Uhat+M");
     join_aux(h);
+    phase_mark(h, "join_Vhat");
     if (sc.is_data) {
         pass_S(h, sc.d, r2, r2, Kh, n, Lh, m, h->Rm, W);
         allreduce_pair(h, h->M, r2, r, h->Rm, r2, r2);
@@ -703,8 +724,10 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
         small_gemm(cx, r2, r2, r, h->T1, (int)W, false, h->N, (int)W, true, h->Sh, (int)W, 1.0, 0.0);
         de_S_flow(h, h->Sh, r2, r2, Kh, Lh, +1.0, sc.t, sc.dt);
     }
+    phase_mark(h, "S_flow_or_pass");
     h->jws.ensure((int64_t)jacobi_ws_doubles(r2), cx.stream);
     jacobi_svd(cx, r2, h->Sh, (int)W, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, tol, rcap, h->r_new_dev, nullptr);
+    phase_mark(h, "core_svd");
     DLRA_CUDA(cudaMemcpyAsync(h->r_new_host, h->r_new_dev, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
     DLRA_CUDA(cudaStreamSynchronize(cx.stream));
     const int r1 = *h->r_new_host;
@@ -713,6 +736,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     gemm_nn(cx, m, r2, r1, Lh, m, nullptr, 0, h->Qm, W, false, h->V, m, 1.0, 0.0);   // V1 = Vhat*Q[:, 1:r1]
     fill_mat(cx, r1, r1, h->S, W, 0.0, 0.0);
     copy_mat(cx, 1, r1, h->sig, 1, false, h->S, W + 1);                              // S1 = Diagonal(sigma[1:r1])
+    phase_mark(h, "new_factors");
     if (changed) *changed = (r1 != r) ? 1 : 0;
     if (r_new_out) *r_new_out = r1;
     h->r = r1;

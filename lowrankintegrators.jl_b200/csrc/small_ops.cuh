@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q,
 }
 
 
+
 // ------------------------------------------------------------------------------------------------
 // Wide Gram-type product (p or q > 16, long n) on the fp64 tensor pipe, ONE launch, A and B streamed ONCE per 64 x 64 output
 // block:  a persistent CTA per SM owns a contiguous range of 32-row tiles, stages [32 rows x 64 cols] of A and of B through a
@@ -224,8 +225,11 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q,
 // (ticket counter) — deterministic, no atomics on data.  Needs 16-byte aligned column starts (even lda/ldb).
 // ------------------------------------------------------------------------------------------------
 constexpr int GT_ROWS = 32, GT_LD = 36, GT_BLK = 64, GT_STAGES = 4;
-constexpr int GT_TILE_DOUBLES = GT_BLK * GT_LD;                                   // one operand tile
-constexpr int GT_SMEM_BYTES = GT_STAGES * 2 * GT_TILE_DOUBLES * (int)sizeof(double);   // 147456
+template <int QB> struct GramTileCfg {   // QB = 64: 64 x 64 output block per CTA; QB = 16: 64 x 16 (BCGS2 projections: q <= 16)
+    static constexpr int TILE_A = GT_BLK * GT_LD, TILE_B = QB * GT_LD;
+    static constexpr int SMEM_BYTES = GT_STAGES * (TILE_A + TILE_B) * (int)sizeof(double);
+    static constexpr int MB = QB == 64 ? 4 : 1;   // 8-row blocks of the output per warp
+};
 
 __device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
     const uint32_t d = smem_u32(smem_dst);
@@ -236,39 +240,46 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+template <int QB>
 __global__ void __launch_bounds__(256, 1) gram_tile_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
                                                            const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
                                                            double alpha, double beta, double* __restrict__ part,
                                                            unsigned int* __restrict__ counters, int64_t tiles_per_cta) {
+    using CF = GramTileCfg<QB>;
+    constexpr int MB = CF::MB;
     extern __shared__ __align__(16) double gts[];
     __shared__ bool is_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;          // warp tile: rows [32 wm, +32) x cols [16 wn, +16) of the 64 x 64 block
-    const int a0 = blockIdx.y * GT_BLK, b0 = blockIdx.z * GT_BLK;
+    // warp tile: QB = 64: rows [32 wm, +32) x cols [16 wn, +16) (2 x 4 warps); QB = 16: rows [8 warp, +8) x all 16 cols
+    const int row_w = QB == 64 ? (warp >> 2) * 32 : warp * 8;
+    const int col_w = QB == 64 ? (warp & 3) * 16 : 0;
+    const int a0 = blockIdx.y * GT_BLK, b0 = blockIdx.z * QB;
     const int64_t ntiles = (n + GT_ROWS - 1) / GT_ROWS;
     const int64_t t0 = (int64_t)blockIdx.x * tiles_per_cta, t1 = min(ntiles, t0 + tiles_per_cta);
-    double acc[4][2][2];
+    double acc[MB][2][2];
 #pragma unroll
-    for (int mb = 0; mb < 4; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb) { acc[mb][nb][0] = 0.0; acc[mb][nb][1] = 0.0; }
 
-    // loader: a tile is 64 columns x 16 chunks of 16 bytes; thread -> (column = e / 16, chunk = e % 16), 4 chunks per operand
+    // loader: an operand tile is (64 | QB) columns x 16 chunks of 16 bytes
     auto issue = [&](int64_t t, int stage) {
-        double* As = gts + (size_t)stage * 2 * GT_TILE_DOUBLES;
-        double* Bs = As + GT_TILE_DOUBLES;
+        double* As = gts + (size_t)stage * (CF::TILE_A + CF::TILE_B);
+        double* Bs = As + CF::TILE_A;
         const int64_t r0 = t * GT_ROWS;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int e = threadIdx.x + it * 256;
             const int col = e >> 4, ch = e & 15;
             const int64_t row = r0 + 2 * ch;
-            const bool rok = row < n;   // n even or the tail element is zero-filled below
-            const bool aok = rok && (a0 + col) < p, bok = rok && (b0 + col) < q;
+            const bool aok = row < n && (a0 + col) < p;
             const double* ga = A + (aok ? row + (int64_t)(a0 + col) * lda : 0);
-            const double* gb = B + (bok ? row + (int64_t)(b0 + col) * ldb : 0);
             cp_async16_zfill(As + col * GT_LD + 2 * ch, ga, aok);
-            cp_async16_zfill(Bs + col * GT_LD + 2 * ch, gb, bok);
+            if (col < QB) {
+                const bool bok = row < n && (b0 + col) < q;
+                const double* gb = B + (bok ? row + (int64_t)(b0 + col) * ldb : 0);
+                cp_async16_zfill(Bs + col * GT_LD + 2 * ch, gb, bok);
+            }
         }
     };
     const int64_t my = t1 > t0 ? t1 - t0 : 0;
@@ -282,36 +293,35 @@ __global__ void __launch_bounds__(256, 1) gram_tile_kernel(int64_t n, int p, int
         __syncthreads();                       // tile i landed for everybody; everybody is done with tile i-1's slot
         if (i + GT_STAGES - 1 < my) issue(t0 + i + GT_STAGES - 1, (int)((i + GT_STAGES - 1) % GT_STAGES));
         cp_async_commit();
-        const double* As = gts + (size_t)(i % GT_STAGES) * 2 * GT_TILE_DOUBLES;
-        const double* Bs = As + GT_TILE_DOUBLES;
-        const double* ap = As + (wm * 32 + g) * GT_LD + k;
-        const double* bp = Bs + (wn * 16 + g) * GT_LD + k;
+        const double* As = gts + (size_t)(i % GT_STAGES) * (CF::TILE_A + CF::TILE_B);
+        const double* Bs = As + CF::TILE_A;
+        const double* ap = As + (row_w + g) * GT_LD + k;
+        const double* bp = Bs + (col_w + g) * GT_LD + k;
 #pragma unroll
         for (int ks = 0; ks < GT_ROWS / 4; ++ks) {
-            double af[4], bf[2];
+            double af[MB], bf[2];
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb) af[mb] = ap[mb * 8 * GT_LD + ks * 4];
+            for (int mb = 0; mb < MB; ++mb) af[mb] = ap[mb * 8 * GT_LD + ks * 4];
 #pragma unroll
             for (int nb = 0; nb < 2; ++nb) bf[nb] = bp[nb * 8 * GT_LD + ks * 4];
 #pragma unroll
-            for (int mb = 0; mb < 4; ++mb)
+            for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
                 for (int nb = 0; nb < 2; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
         }
     }
     cp_async_wait<0>();
-    // an odd n leaves the last element of a 16-byte chunk beyond the matrix: it was loaded (aligned chunk inside the padded
-    // column) only when row+1 < n is guaranteed by the host-side check n % 2 == 0
     const int nblk = gridDim.x;
     const int slot = blockIdx.y * gridDim.z + blockIdx.z;
-    double* mypart = part + ((int64_t)slot * nblk + blockIdx.x) * (GT_BLK * GT_BLK);
+    constexpr int PART = GT_BLK * QB;
+    double* mypart = part + ((int64_t)slot * nblk + blockIdx.x) * PART;
 #pragma unroll
-    for (int mb = 0; mb < 4; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int nb = 0; nb < 2; ++nb)
 #pragma unroll
             for (int e = 0; e < 2; ++e)
-                mypart[(wm * 32 + mb * 8 + g) + GT_BLK * (wn * 16 + nb * 8 + 2 * k + e)] = acc[mb][nb][e];
+                mypart[(row_w + mb * 8 + g) + GT_BLK * (col_w + nb * 8 + 2 * k + e)] = acc[mb][nb][e];
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -321,12 +331,12 @@ __global__ void __launch_bounds__(256, 1) gram_tile_kernel(int64_t n, int p, int
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const double* base = part + (int64_t)slot * nblk * (GT_BLK * GT_BLK);
-    for (int e = threadIdx.x; e < GT_BLK * GT_BLK; e += 256) {
+    const double* base = part + (int64_t)slot * nblk * PART;
+    for (int e = threadIdx.x; e < PART; e += 256) {
         const int i = e % GT_BLK, j = e / GT_BLK;
         if (a0 + i >= p || b0 + j >= q) continue;
         double s = 0.0;
-        for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * (GT_BLK * GT_BLK) + e);
+        for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * PART + e);
         double* dst = C + (a0 + i) + (int64_t)(b0 + j) * ldc;
         *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
     }
@@ -352,7 +362,7 @@ inline bool gram_fast_ok(const Ctx& cx, int p, int q) { return cx.counters != nu
 inline int64_t gemm_tn_ws(const Ctx& cx, int64_t n, int p, int q) {
     const int64_t generic = gemm_tn_chunks(cx, n, p, q) * p * q;
     const int64_t fast = cdiv(p, 16) * cdiv(q, 16) * cdiv(n, GRAM_ROWS_PER_CTA) * 256;
-    const int64_t tiled = cdiv(p, GT_BLK) * cdiv(q, GT_BLK) * (int64_t)gram_tile_ctas(cx, n) * GT_BLK * GT_BLK;
+    const int64_t tiled = cdiv(p, GT_BLK) * (int64_t)gram_tile_ctas(cx, n) * GT_BLK * (q <= 16 ? 16 : cdiv(q, GT_BLK) * GT_BLK);
     return std::max(std::max(generic, fast), tiled);
 }
 
@@ -362,12 +372,19 @@ inline void gemm_tn(Ctx& cx, int64_t n, int p, int q, const double* A, int64_t l
     if (p <= 0 || q <= 0) return;
     if (!Aprev && gram_tile_ok(cx, n, p, q, A, lda, B, ldb)) {
         static unsigned long long attr_devs = 0;
-        if (first_use_on_this_device(attr_devs))
-            DLRA_CUDA(cudaFuncSetAttribute(gram_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES));
+        if (first_use_on_this_device(attr_devs)) {
+            DLRA_CUDA(cudaFuncSetAttribute(gram_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramTileCfg<64>::SMEM_BYTES));
+            DLRA_CUDA(cudaFuncSetAttribute(gram_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GramTileCfg<16>::SMEM_BYTES));
+        }
         const int G = gram_tile_ctas(cx, n);
         const int64_t tiles_per_cta = cdiv(cdiv(n, GT_ROWS), G);
-        dim3 grid((unsigned)G, (unsigned)cdiv(p, GT_BLK), (unsigned)cdiv(q, GT_BLK));
-        gram_tile_kernel<<<grid, 256, GT_SMEM_BYTES, cx.stream>>>(n, p, q, A, lda, B, ldb, C, ldc, alpha, beta, ws, cx.counters, tiles_per_cta);
+        if (q <= 16) {   // narrow right-hand side (BCGS2 projections): a 64 x 16 block per CTA, a quarter of the DMMA work of the square block
+            dim3 grid((unsigned)G, (unsigned)cdiv(p, GT_BLK), 1);
+            gram_tile_kernel<16><<<grid, 256, GramTileCfg<16>::SMEM_BYTES, cx.stream>>>(n, p, q, A, lda, B, ldb, C, ldc, alpha, beta, ws, cx.counters, tiles_per_cta);
+        } else {
+            dim3 grid((unsigned)G, (unsigned)cdiv(p, GT_BLK), (unsigned)cdiv(q, GT_BLK));
+            gram_tile_kernel<64><<<grid, 256, GramTileCfg<64>::SMEM_BYTES, cx.stream>>>(n, p, q, A, lda, B, ldb, C, ldc, alpha, beta, ws, cx.counters, tiles_per_cta);
+        }
         cx.launches++;
         DLRA_CUDA(cudaGetLastError());
         return;

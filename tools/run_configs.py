@@ -95,12 +95,13 @@ def cfg4():
     eng.rhs_set(A=csr_dev(A), B=csr_dev(B), G=lri.colmajor_device(G), H=lri.colmajor_device(H))
     for f in (L.FLOW_K, L.FLOW_S, L.FLOW_L): eng.set_substepper(f, L.ODE_RK4, 1)
     t = 0.0
-    for k in range(8):
+    for k in range(int(os.environ.get('CFG4_STEPS', '8'))):
         eng.sync(); t0 = time.perf_counter()
         rn, ch = eng.step_rabug(1e-8, 128, t, 1e-6)
         eng.sync(); ms = (time.perf_counter() - t0) * 1e3
         t += 1e-6
         print(f"cfg4 Lyapunov n=m={n} RA-BUG step {k}: rank -> {rn} ({ms:.1f} ms)", flush=True)
+        if os.environ.get("DLRA_PHASES"): eng.stats()
     eng.close()
 
 
