@@ -766,6 +766,18 @@ static void greedy_step(dlra_handle h, const Delta& x) {
     std::swap(h->V, h->VB);
 }
 
+// Orthonormal completion of the left singular vectors of a small core (r x r, ld W), in place.  The one-sided Jacobi sweep never
+// rotates column pairs below the rounding floor of the matrix, so the columns of P that belong to (numerically) zero singular values
+// come out normalised but NOT orthogonal to the others, whereas LAPACK's svd (greedy_integrator.jl:88) always returns an orthonormal P.
+// Householder QR of P with the signs of diag(R) folded back reproduces the converged leading columns to rounding (their R block is
+// diag(+-1)) and replaces the rest by an orthonormal completion.  Uses Rm as scratch.
+static void ortho_complete(dlra_handle h, double* P, int r) {
+    Side sd = main_side(h);
+    ensure_qr_ws(sd, r, r);
+    thin_qr(h->cx, h->self, r, r, P, h->W, P, h->W, h->Rm, h->W, sd.tws->p, sd.gws->p, sd.wtmp->p);
+    sign_fix_cols(h->cx, r, r, P, h->W, h->Rm, h->W);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // greedy step of the two-factor representation u = U*Z' — greedy_integrator.jl:72-92
 // Z lives in the V slot, S stays at identity.
@@ -791,6 +803,7 @@ static void greedy_two_factor_step(dlra_handle h, const Delta& x, int mode, bool
     qr_nside(h, XZ, r, h->Rm);
     h->jws.ensure((int64_t)jacobi_ws_doubles(r), cx.stream);
     jacobi_svd(cx, r, h->Rm, (int)W, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, 0.0, r, nullptr, nullptr);
+    ortho_complete(h, h->Pm, r);   // rank(X*Z) < r: the polar factor must still be orthonormal
     small_gemm(cx, r, r, r, h->Pm, (int)W, false, h->Qm, (int)W, true, h->T1, (int)W, 1.0, 0.0);
     gemm_nn(cx, n, r, r, XZ, n, nullptr, 0, h->T1, W, false, h->U, n, 1.0, 0.0);              // mul!(U, Q, P')
     std::swap(h->V, h->VB);

@@ -533,6 +533,22 @@ inline void fill_mat(Ctx& cx, int64_t rows, int cols, double* dst, int64_t ldd, 
     DLRA_CUDA(cudaGetLastError());
 }
 
+// Q[:, j] *= sign(R[j, j])  (R[j, j] == 0 keeps the column): turns the Q of a Householder QR of an (almost) orthonormal matrix
+// back into that matrix, see ortho_complete in engine.cu
+__global__ void sign_fix_cols_kernel(int rows, int cols, double* __restrict__ Q, int64_t ldq, const double* __restrict__ R, int64_t ldr) {
+    const int tot = rows * cols;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += gridDim.x * blockDim.x) {
+        const int i = e % rows, j = e / rows;
+        if (R[j + (int64_t)j * ldr] < 0.0) Q[i + (int64_t)j * ldq] = -Q[i + (int64_t)j * ldq];
+    }
+}
+inline void sign_fix_cols(Ctx& cx, int rows, int cols, double* Q, int64_t ldq, const double* R, int64_t ldr) {
+    if (rows <= 0 || cols <= 0) return;
+    sign_fix_cols_kernel<<<(unsigned)std::min<int64_t>(cdiv((int64_t)rows * cols, 256), 1024), 256, 0, cx.stream>>>(rows, cols, Q, ldq, R, ldr);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
+}
+
 // ------------------------------------------------------------------------------------------------
 // sum_{i,j} (X[i,:]·W[j,:] - Yref[i,j])^2 and sum Yref^2  (X = U*S n x r, W = V m x r) -> out[2] partial per block
 // ------------------------------------------------------------------------------------------------

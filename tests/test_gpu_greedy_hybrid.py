@@ -42,6 +42,26 @@ def test_two_factor_greedy_data(lri, n, m, r):
         assert rel_fro(gu.Z, ou.Z) <= TOL and np.linalg.norm(gu.U.T @ gu.U - np.eye(r)) < 1e-12
 
 
+@pytest.mark.parametrize("n,m,r,deficit", [(384, 256, 6, 2), (4096, 512, 8, 3)])
+def test_two_factor_greedy_rank_deficient_data(lri, n, m, r, deficit):
+    # rank(X) < r: svd(X*Z) has zero singular values; the reference's polar factor Q*P' is orthonormal all the same
+    # (U*Z' does not depend on the completion).  The one-sided Jacobi core SVD leaves the null-space columns of P non-orthogonal -> ortho_complete.
+    rng = np.random.default_rng(5)
+    s = r - deficit
+    L0, R0 = rng.standard_normal((n, s)), rng.standard_normal((m, s))
+    L1, R1 = rng.standard_normal((n, s)), rng.standard_normal((m, s))
+    snaps = [(L0 + 0.05 * k * L1) @ (R0 + 0.05 * k * R1).T for k in range(5)]
+    U0, Z0 = two_factor_start(snaps[0], r)
+    gint = lri.init(lri.MatrixDataProblem(snaps, lri.TwoFactorRepresentation(U0, Z0)), lri.GreedyIntegrator(), 1)
+    oint = O.init(O.MatrixDataProblem(snaps, O.TwoFactorRepresentation(U0, Z0)), O.GreedyIntegrator(), 1)
+    for k in range(4):
+        O.step(oint)
+        lri.step(gint)
+        gu, ou = gint.u, oint.u
+        assert np.linalg.norm(gu.U.T @ gu.U - np.eye(r)) < 1e-12, k
+        assert rel_fro(gu.full(), ou.full()) <= TOL, k
+
+
 def hybrid_pair(lri, y, grhs, of, U0, Z0, tf, dt, sub, carry):
     galg = lri.GreedyIntegrator(Z_alg=lri.SubStepper(*sub), fsal_carry=carry)
     oalg = O.GreedyIntegrator(Z_alg=O.SubStepper(*sub), fsal_carry=carry)
