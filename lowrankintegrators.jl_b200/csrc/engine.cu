@@ -63,6 +63,7 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         e->ax.num_sms = e->cx.num_sms;
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
+        DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_rnew, cudaEventDisableTiming));
         const int64_t W = e->W;
         auto dmalloc = [&](int64_t doubles) {
             double* p = nullptr;
@@ -136,6 +137,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     h->gws2.release(); h->tws2.release(); h->wtmp2.release(); h->zcarry.k.release();
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_rnew) cudaEventDestroy(h->ev_rnew);
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     if (h->cx.stream) cudaStreamDestroy(h->cx.stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -228,6 +230,7 @@ static void set_factors_impl(dlra_handle h, const double* U, int64_t ldu, const 
     h->r = r;
     h->kl_ready = false;   // a precomputed K/L pass belongs to the factors it was formed with
     h->zcarry.valid = false;
+    h->basis_trusted = false;   // user-supplied bases: the next rank-adaptive step factors the whole augmented basis
     if (kind == cudaMemcpyHostToDevice) DLRA_CUDA(cudaStreamSynchronize(s));
 }
 extern "C" int dlra_set_factors_host(dlra_handle h, const double* U, int64_t ldu, const double* S, int64_t lds, const double* V,
@@ -566,6 +569,16 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
             tri_pass_launch(h, h->nxt, h->ldnxt, sc.d.A, sc.d.lda, sc.d.Aprev, sc.d.ldap, r, L, m, K, n, h->nscr.p, n,
                             h->U /* old U0 buffer: the next step's K */, n, h->part.p, ldlp, nsub, npanels);
             h->gws.ensure(gemm_tn_ws(cx, n, r, r), cx.stream);
+            static const bool fused_core = !(getenv("DLRA_FUSED_CORE") && atoi(getenv("DLRA_FUSED_CORE")) == 0);
+            if (fused_core && h->comm.nranks <= 1 && r <= 16 && cx.counters) {
+                // Rm = U1'*W and S1 = M*S0*N' + Rm in one launch (same arithmetic as the two kernels below)
+                h->kl_ready = true; h->kl_nparts = nparts; h->kl_ldlp = ldlp; h->kl_rank = r;
+                gram_core(cx, n, r, K, n, h->nscr.p, n, h->Rm, h->gws.p, h->M, h->S, h->N, h->S, (int)W);
+                phase_mark(h, "pass_S(+KL_next)+gram+core");
+                std::swap(h->U, h->UB);
+                std::swap(h->V, h->VB);
+                return;
+            }
             gemm_tn(cx, n, r, r, K, n, nullptr, 0, h->nscr.p, n, h->Rm, W, 1.0, 0.0, h->gws.p);   // Rm = U1'*W (local rows)
             h->kl_ready = true; h->kl_nparts = nparts; h->kl_ldlp = ldlp; h->kl_rank = r;
             phase_mark(h, "pass_S(+KL_next)+gram");
@@ -690,6 +703,8 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     double *Kh = h->UB, *Lh = h->VB;   // [K U0] -> Uhat ; [L V0] -> Vhat
     // DLRA_AUG_BASIS_FIRST: [U0 K], [V0 L] — same span; the leading (orthonormal) panel then skips its factorisation
     const bool first = (h->flags & DLRA_AUG_BASIS_FIRST) != 0;
+    const int ortho_lead = (first && h->basis_trusted && (h->aug_steps % dlra_engine::AUG_REORTHO_EVERY) != dlra_engine::AUG_REORTHO_EVERY - 1) ? r : 0;
+    h->aug_steps++;
     double* Kc = first ? Kh + (int64_t)r * n : Kh;          // where K / L are formed
     double* Lc = first ? Lh + (int64_t)r * m : Lh;
     double* Uc = first ? Kh : Kh + (int64_t)r * n;          // where the copies of U0 / V0 go
@@ -706,9 +721,9 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     copy_mat(cx, m, r, h->V, m, false, Vc, m);
     phase_mark(h, "KL_flows");
     fork_aux(h);
-    qr_mside(h, aux_side(h), Lh, r2, nullptr, first ? r : 0);
+    qr_mside(h, aux_side(h), Lh, r2, nullptr, ortho_lead);
     gram_mside(h, aux_side(h), r2, r, Lh, h->V, h->N);                   // N = Vhat'*V0
-    qr_nside(h, Kh, r2, nullptr, first ? r : 0);
+    qr_nside(h, Kh, r2, nullptr, ortho_lead);
     gram_nside_local(h, r2, r, Kh, h->U, h->M);                          // M = Uhat'*U0 (2r x r), local rows
     phase_mark(h, "qr_Uhat+M");
     join_aux(h);
@@ -726,17 +741,33 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     }
     phase_mark(h, "S_flow_or_pass");
     h->jws.ensure((int64_t)jacobi_ws_doubles(r2), cx.stream);
-    jacobi_svd(cx, r2, h->Sh, (int)W, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, tol, rcap, h->r_new_dev, nullptr);
+    static const bool jacobi_pre = !(getenv("DLRA_JACOBI_PRE") && atoi(getenv("DLRA_JACOBI_PRE")) == 0);
+    if (jacobi_pre) {
+        // Shat = Q0*R (Householder, in place), then Jacobi on R' with the accumulator started at Q0 (jacobi.cuh)
+        double* Rj = jacobi_ws_rfactor(h->jws.p, r2);
+        Side sd = main_side(h);
+        ensure_qr_ws(sd, r2, r2);
+        thin_qr(cx, h->self, r2, r2, h->Sh, W, h->Sh, W, Rj, r2, sd.tws->p, sd.gws->p, sd.wtmp->p);
+        phase_mark(h, "core_qr");
+        jacobi_svd(cx, r2, Rj, r2, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, tol, rcap, h->r_new_dev, nullptr, h->Sh, (int)W);
+    } else {
+        jacobi_svd(cx, r2, h->Sh, (int)W, h->jws.p, h->Pm, (int)W, h->sig, h->Qm, (int)W, tol, rcap, h->r_new_dev, nullptr);
+    }
     phase_mark(h, "core_svd");
+    // The host needs the new rank (it sizes every later launch), but nothing that follows on the device does: the basis update runs
+    // at the full candidate width rcap (columns beyond r1 are never read: the factor buffers are W wide) and is enqueued BEFORE the
+    // host waits, so the device stays busy during the round trip and the host resumes as soon as the SVD — not the whole step — is done.
     DLRA_CUDA(cudaMemcpyAsync(h->r_new_host, h->r_new_dev, sizeof(int), cudaMemcpyDeviceToHost, cx.stream));
-    DLRA_CUDA(cudaStreamSynchronize(cx.stream));
+    DLRA_CUDA(cudaEventRecord(h->ev_rnew, cx.stream));
+    gemm_nn(cx, n, r2, rcap, Kh, n, nullptr, 0, h->Pm, W, false, h->U, n, 1.0, 0.0);   // U1 = Uhat*P[:, 1:r1]
+    gemm_nn(cx, m, r2, rcap, Lh, m, nullptr, 0, h->Qm, W, false, h->V, m, 1.0, 0.0);   // V1 = Vhat*Q[:, 1:r1]
+    fill_mat(cx, rcap, rcap, h->S, W, 0.0, 0.0);
+    copy_mat(cx, 1, rcap, h->sig, 1, false, h->S, W + 1);                              // S1 = Diagonal(sigma[1:r1]) (leading block)
+    phase_mark(h, "new_factors");
+    DLRA_CUDA(cudaEventSynchronize(h->ev_rnew));
     const int r1 = *h->r_new_host;
     DLRA_REQUIRE(r1 >= 1 && r1 <= rcap, "rank selection returned an impossible rank");
-    gemm_nn(cx, n, r2, r1, Kh, n, nullptr, 0, h->Pm, W, false, h->U, n, 1.0, 0.0);   // U1 = Uhat*P[:, 1:r1]
-    gemm_nn(cx, m, r2, r1, Lh, m, nullptr, 0, h->Qm, W, false, h->V, m, 1.0, 0.0);   // V1 = Vhat*Q[:, 1:r1]
-    fill_mat(cx, r1, r1, h->S, W, 0.0, 0.0);
-    copy_mat(cx, 1, r1, h->sig, 1, false, h->S, W + 1);                              // S1 = Diagonal(sigma[1:r1])
-    phase_mark(h, "new_factors");
+    h->basis_trusted = true;
     if (changed) *changed = (r1 != r) ? 1 : 0;
     if (r_new_out) *r_new_out = r1;
     h->r = r1;

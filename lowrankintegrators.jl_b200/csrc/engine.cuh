@@ -72,6 +72,13 @@ struct dlra_engine {
     dlra::Ctx cx;
     dlra::Ctx ax;               // auxiliary stream: the replicated m-side chain (QR(L), N) overlaps the n-side chain (QR(K), M)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ext = nullptr;
+    cudaEvent_t ev_rnew = nullptr;      // rank-adaptive step: the new rank has landed in r_new_host
+    // DLRA_AUG_BASIS_FIRST takes the leading panel [U0], [V0] of the augmented bases as orthonormal: true for factors produced by a
+    // step of this engine, unknown for factors handed in through dlra_set_factors; every AUG_REORTHO_EVERY-th step factors the whole
+    // augmented basis anyway so that the orthogonality defect cannot accumulate over long runs
+    bool basis_trusted = false;
+    int64_t aug_steps = 0;
+    static constexpr int AUG_REORTHO_EVERY = 256;
     dlra::Comm comm;            // row-shard communicator
     dlra::Comm self;            // nranks = 1: for replicated (m-side) factorizations
     cudaStream_t copy_stream = nullptr;

@@ -206,13 +206,106 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q,
     __threadfence();
     double s = 0.0;
     const double* base = part + (int64_t)slot * nblk * 256 + threadIdx.x;
-    for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * 256);
+#pragma unroll 8
+    for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * 256);   // loads batched, additions in block order
     const int i = threadIdx.x % 16, j = threadIdx.x / 16;
     if (a0 + i < p && b0 + j < q) {
         double* dst = C + (a0 + i) + (int64_t)(b0 + j) * ldc;
         *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
     }
     if (threadIdx.x == 0) counters[slot] = 0;   // self-reset for the next launch on this stream
+}
+
+// The tail of the pipelined BUG step in ONE launch (single GPU):  Rm = A'·B  (A = U1, B = ΔA·V1: the core increment, r <= 16) with the
+// arithmetic of gram_dmma_kernel, and — in the last CTA to finish — the core update  Out = M·S0·N' + Rm  with the arithmetic of
+// core_update_kernel (unconventional.jl:154-155).  Saves a launch and the round trip of Rm through global memory on the critical path
+// between the streaming pass and the next step's QR.  Out may alias S0.
+__global__ void __launch_bounds__(256) gram_core_kernel(int64_t n, int r, const double* __restrict__ A, int64_t lda,
+                                                        const double* __restrict__ B, int64_t ldb, double* __restrict__ Rm,
+                                                        double* __restrict__ part, unsigned int* __restrict__ counters,
+                                                        const double* __restrict__ M, const double* S0,
+                                                        const double* __restrict__ Nn, double* Out, int ld) {
+    __shared__ double red[8][256];
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k = lane & 3;
+    const int64_t r0 = (int64_t)blockIdx.x * GRAM_ROWS_PER_CTA, r1 = min(n, r0 + GRAM_ROWS_PER_CTA);
+    double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+    const bool c_ok[2] = {g < r, 8 + g < r};
+    const double* Ap[2] = {A + (int64_t)g * lda, A + (int64_t)(8 + g) * lda};
+    const double* Bp[2] = {B + (int64_t)g * ldb, B + (int64_t)(8 + g) * ldb};
+#pragma unroll 4
+    for (int64_t row = r0 + 4 * warp; row < r1; row += 32) {
+        const int64_t i = row + k;
+        const bool ok = i < r1;
+        double af[2], bf[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            af[h] = (ok && c_ok[h]) ? Ap[h][i] : 0.0;
+            bf[h] = (ok && c_ok[h]) ? Bp[h][i] : 0.0;
+        }
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+            for (int nb = 0; nb < 2; ++nb) dmma884(acc[mb][nb][0], acc[mb][nb][1], af[mb], bf[nb]);
+    }
+#pragma unroll
+    for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+        for (int nb = 0; nb < 2; ++nb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) red[warp][(mb * 8 + g) + 16 * (nb * 8 + 2 * k + e)] = acc[mb][nb][e];
+    __syncthreads();
+    const int nblk = gridDim.x;
+    {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+        part[(int64_t)blockIdx.x * 256 + threadIdx.x] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&counters[0], 1u);
+        is_last = (ticket == (unsigned int)nblk - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // operands of the core update: staged while the partial sums are in flight
+    double (*sM)[17] = reinterpret_cast<double (*)[17]>(&red[0][0]);        // red is dead: 4 x 16 x 17 doubles fit in its first rows
+    double (*sS)[17] = sM + 16;
+    double (*sN)[17] = sS + 16;
+    double (*sT)[17] = sN + 16;
+    const int i = threadIdx.x % 16, j = threadIdx.x / 16;
+    const bool in = i < r && j < r;
+    sM[i][j] = in ? M[i + (int64_t)j * ld] : 0.0;
+    sS[i][j] = in ? S0[i + (int64_t)j * ld] : 0.0;
+    sN[i][j] = in ? Nn[i + (int64_t)j * ld] : 0.0;
+    double s = 0.0;
+    const double* base = part + threadIdx.x;
+#pragma unroll 8
+    for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * 256);   // fixed block order, as gram_dmma_kernel
+    s = 0.0 + 1.0 * s;
+    if (in) Rm[i + (int64_t)j * ld] = s;
+    __syncthreads();
+    {   // T = M*S0 (thread <-> T[i][j])
+        double t = 0.0;
+        for (int l = 0; l < r; ++l) t = fma(sM[i][l], sS[l][j], t);
+        sT[i][j] = t;
+    }
+    __syncthreads();
+    {
+        double t = 0.0;
+        for (int l = 0; l < r; ++l) t = fma(sT[i][l], sN[j][l], t);
+        if (in) Out[i + (int64_t)j * ld] = t + s;
+    }
+    if (threadIdx.x == 0) counters[0] = 0;
+}
+inline void gram_core(Ctx& cx, int64_t n, int r, const double* A, int64_t lda, const double* B, int64_t ldb, double* Rm, double* ws,
+                      const double* M, const double* S0, const double* Nn, double* Out, int ld) {
+    gram_core_kernel<<<(unsigned)cdiv(n, GRAM_ROWS_PER_CTA), 256, 0, cx.stream>>>(n, r, A, lda, B, ldb, Rm, ws, cx.counters, M, S0, Nn, Out, ld);
+    cx.launches++;
+    DLRA_CUDA(cudaGetLastError());
 }
 
 
@@ -336,6 +429,7 @@ __global__ void __launch_bounds__(256, 1) gram_tile_kernel(int64_t n, int p, int
         const int i = e % GT_BLK, j = e / GT_BLK;
         if (a0 + i >= p || b0 + j >= q) continue;
         double s = 0.0;
+#pragma unroll 8
         for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * PART + e);
         double* dst = C + (a0 + i) + (int64_t)(b0 + j) * ldc;
         *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;

@@ -90,7 +90,7 @@ def cfg4():
     A = sum(periodic_ops(n, nu=0.02)); B = sum(periodic_ops(m, nu=0.03))
     q = 128
     G = orth(n, q, g); H = orth(m, q, g) * (0.7 ** torch.arange(q, device=dev, dtype=torch.float64))
-    eng = lri.Engine(n, m, 8, rmax=128, rank_adaptive=True)
+    eng = lri.Engine(n, m, 8, rmax=128, rank_adaptive=True, aug_basis_first=os.environ.get('CFG4_AUG') == '1')
     eng.set_factors(orth(n, 8, g), torch.diag(2.0 ** -torch.arange(8, device=dev, dtype=torch.float64)), orth(m, 8, g))
     eng.rhs_set(A=csr_dev(A), B=csr_dev(B), G=lri.colmajor_device(G), H=lri.colmajor_device(H))
     for f in (L.FLOW_K, L.FLOW_S, L.FLOW_L): eng.set_substepper(f, L.ODE_RK4, 1)
