@@ -57,13 +57,19 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         e->n = n_local; e->m = m; e->r = r0; e->rmax = rmax; e->flags = flags;
         e->W = (flags & DLRA_RANK_ADAPTIVE) ? 2 * rmax : rmax;
         e->cx.num_sms = prop.multiProcessorCount;
-        DLRA_CUDA(cudaStreamCreateWithFlags(&e->cx.stream, cudaStreamNonBlocking));
+        // the main stream outranks the auxiliary one: when both have CTAs pending (the streaming pass and a small m-side / Gram
+        // kernel that became ready at the same moment) the pass gets the SMs first
+        int prio_least = 0, prio_greatest = 0;
+        DLRA_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        DLRA_CUDA(cudaStreamCreateWithPriority(&e->cx.stream, cudaStreamNonBlocking, prio_greatest));
         DLRA_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-        DLRA_CUDA(cudaStreamCreateWithFlags(&e->ax.stream, cudaStreamNonBlocking));
+        DLRA_CUDA(cudaStreamCreateWithPriority(&e->ax.stream, cudaStreamNonBlocking, prio_least));
         e->ax.num_sms = e->cx.num_sms;
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_rnew, cudaEventDisableTiming));
+        DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_kqr, cudaEventDisableTiming));
+        DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
         const int64_t W = e->W;
         auto dmalloc = [&](int64_t doubles) {
             double* p = nullptr;
@@ -138,6 +144,9 @@ extern "C" int dlra_destroy(dlra_handle h) {
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_rnew) cudaEventDestroy(h->ev_rnew);
+    if (h->ev_kqr) cudaEventDestroy(h->ev_kqr);
+    if (h->ev_join2) cudaEventDestroy(h->ev_join2);
+    h->UC.release();
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
     if (h->cx.stream) cudaStreamDestroy(h->cx.stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -542,21 +551,36 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
         de_L_flow(h, L, r, h->U, sc.t, sc.dt);
     }
     phase_mark(h, "KL_or_Lsum");
+    const bool pipe = sc.is_data && !(h->flags & DLRA_FORCE_GENERIC) && h->have_nxt && h->nxt_kind == DLRA_DATA_SNAPSHOT &&
+                      sc.d.Aprev != nullptr && r <= 16 && tma_pass_supported(n, m, sc.d) && tma_ok(h->nxt, h->ldnxt);
+    // Single GPU, pipelined pass: M = U1'*U0 leaves the critical path.  It runs on the auxiliary stream BESIDE the streaming pass
+    // (which then writes the next step's K into a third buffer instead of the buffer of U0) and is only needed by the core update.
+    static const bool gram_m_aux = !(getenv("DLRA_GRAM_M_AUX") && atoi(getenv("DLRA_GRAM_M_AUX")) == 0);
+    const bool m_aux = pipe && gram_m_aux && h->comm.nranks <= 1;
     fork_aux(h);                                          // m-side chain on the auxiliary stream ...
     if (lfin_aux) l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, 16, 1, h->V, m, h->S, W, r, L, m, &h->ax);
     qr_mside(h, aux_side(h), L, r, nullptr);              // V1 = qr(L).Q
     gram_mside(h, aux_side(h), r, r, L, h->V, h->N);      // N = V1'*V0
+    if (m_aux) DLRA_CUDA(cudaEventRecord(h->ev_join, h->ax.stream));   // the m-side is complete here
     if (pre) qr_nside_plus(h, K, r, h->U, h->S, r);       // ... overlaps U1 = qr(ΔA*V0 + U0*S0).Q
     else qr_nside(h, K, r, nullptr);                      //              U1 = qr(K).Q
     phase_mark(h, "qr_K");
-    // M must be formed BEFORE the pipelined pass: that pass writes the next step's K into the buffer of U0
-    gram_nside_local(h, r, r, K, h->U, h->M);             // M = U1'*U0 (local rows; summed over ranks below)
-    phase_mark(h, "gram_M");
-    join_aux(h);
+    if (m_aux) {
+        h->UC.ensure(n * W, cx.stream);
+        DLRA_CUDA(cudaEventRecord(h->ev_kqr, cx.stream));
+        DLRA_CUDA(cudaStreamWaitEvent(h->ax.stream, h->ev_kqr, 0));
+        h->gws2.ensure(gemm_tn_ws(h->ax, n, r, r), h->ax.stream);
+        gemm_tn(h->ax, n, r, r, K, n, nullptr, 0, h->U, n, h->M, W, 1.0, 0.0, h->gws2.p);   // M = U1'*U0 beside the pass
+        DLRA_CUDA(cudaEventRecord(h->ev_join2, h->ax.stream));
+        DLRA_CUDA(cudaStreamWaitEvent(cx.stream, h->ev_join, 0));
+    } else {
+        // M must be formed BEFORE the pipelined pass: that pass writes the next step's K into the buffer of U0
+        gram_nside_local(h, r, r, K, h->U, h->M);         // M = U1'*U0 (local rows; summed over ranks below)
+        phase_mark(h, "gram_M");
+        join_aux(h);
+    }
     phase_mark(h, "join_Lside");
     if (sc.is_data) {
-        const bool pipe = !(h->flags & DLRA_FORCE_GENERIC) && h->have_nxt && h->nxt_kind == DLRA_DATA_SNAPSHOT && sc.d.Aprev != nullptr &&
-                          r <= 16 && tma_pass_supported(n, m, sc.d) && tma_ok(h->nxt, h->ldnxt);
         if (pipe) {
             // one sweep over A(t), A(t+dt), A(t+2dt): W = ΔA_k*V1 (this step's core) and ΔA_{k+1}*V1, ΔA_{k+1}'*U1 (next step)
             if (h->nxt_own >= 0) DLRA_CUDA(cudaStreamWaitEvent(cx.stream, h->own_ready[h->nxt_own], 0));
@@ -566,8 +590,10 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
             const int64_t ldlp = round_up(m, 2);
             h->part.ensure((int64_t)nparts * ldlp * 16, cx.stream);
             h->nscr.ensure(n * (int64_t)r, cx.stream);
+            double* Knext = m_aux ? h->UC.p : h->U;   // the next step's K: third buffer, or the (no longer needed) buffer of U0
             tri_pass_launch(h, h->nxt, h->ldnxt, sc.d.A, sc.d.lda, sc.d.Aprev, sc.d.ldap, r, L, m, K, n, h->nscr.p, n,
-                            h->U /* old U0 buffer: the next step's K */, n, h->part.p, ldlp, nsub, npanels);
+                            Knext, n, h->part.p, ldlp, nsub, npanels);
+            if (m_aux) DLRA_CUDA(cudaStreamWaitEvent(cx.stream, h->ev_join2, 0));   // M is needed from here on
             h->gws.ensure(gemm_tn_ws(cx, n, r, r), cx.stream);
             static const bool fused_core = !(getenv("DLRA_FUSED_CORE") && atoi(getenv("DLRA_FUSED_CORE")) == 0);
             if (fused_core && h->comm.nranks <= 1 && r <= 16 && cx.counters) {
@@ -575,7 +601,8 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
                 h->kl_ready = true; h->kl_nparts = nparts; h->kl_ldlp = ldlp; h->kl_rank = r;
                 gram_core(cx, n, r, K, n, h->nscr.p, n, h->Rm, h->gws.p, h->M, h->S, h->N, h->S, (int)W);
                 phase_mark(h, "pass_S(+KL_next)+gram+core");
-                std::swap(h->U, h->UB);
+                std::swap(h->U, h->UB);                       // U = U1, UB = buffer of U0
+                if (m_aux) std::swap(h->UB, h->UC.p);         // UB = next step's K, UC = buffer of U0 (free)
                 std::swap(h->V, h->VB);
                 return;
             }
@@ -595,6 +622,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
             }
             phase_mark(h, "core_update");
             std::swap(h->U, h->UB);
+            if (m_aux) std::swap(h->UB, h->UC.p);
             std::swap(h->V, h->VB);
             return;
         } else {
@@ -742,7 +770,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
     phase_mark(h, "S_flow_or_pass");
     h->jws.ensure((int64_t)jacobi_ws_doubles(r2), cx.stream);
     static const bool jacobi_pre = !(getenv("DLRA_JACOBI_PRE") && atoi(getenv("DLRA_JACOBI_PRE")) == 0);
-    if (jacobi_pre) {
+    if (jacobi_pre && r2 >= 64) {   // measured: the small QR costs more than the sweeps it saves below 64 x 64
         // Shat = Q0*R (Householder, in place), then Jacobi on R' with the accumulator started at Q0 (jacobi.cuh)
         double* Rj = jacobi_ws_rfactor(h->jws.p, r2);
         Side sd = main_side(h);

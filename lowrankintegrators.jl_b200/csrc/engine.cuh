@@ -73,6 +73,8 @@ struct dlra_engine {
     dlra::Ctx ax;               // auxiliary stream: the replicated m-side chain (QR(L), N) overlaps the n-side chain (QR(K), M)
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ext = nullptr;
     cudaEvent_t ev_rnew = nullptr;      // rank-adaptive step: the new rank has landed in r_new_host
+    cudaEvent_t ev_kqr = nullptr, ev_join2 = nullptr;   // pipelined BUG step: K-side QR done (main) / M = U1'U0 done (auxiliary)
+    dlra::DevBuf UC;                    // third n x W factor buffer of the pipelined BUG step (allocated on first use)
     // DLRA_AUG_BASIS_FIRST takes the leading panel [U0], [V0] of the augmented bases as orthonormal: true for factors produced by a
     // step of this engine, unknown for factors handed in through dlra_set_factors; every AUG_REORTHO_EVERY-th step factors the whole
     // augmented basis anyway so that the orthogonality defect cannot accumulate over long runs

@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
         double s = 0.0;
         // factor column c lives in the partial of cluster rank c / rt (rt columns per CTA), local column c % rt
         const double* pp = part + (int64_t)(c / rt) * ldlp * rt + j + (int64_t)(c % rt) * ldlp;
-#pragma unroll 8
+#pragma unroll 16
         for (int p = 0; p < nparts; ++p) s += pp[(int64_t)p * part_stride];
         if (XR == 2) ll_push(lv, e, s);
         else if (XR == 1) v.data_local[e] = s;

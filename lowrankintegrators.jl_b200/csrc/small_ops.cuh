@@ -149,6 +149,23 @@ inline void reduce_parts(Ctx& cx, int p, int q, int nchunks, const double* part,
 // tiles are summed in shared memory, every CTA stores one partial and the LAST CTA to finish (ticket counter) adds the
 // partials in fixed order — deterministic without a second launch.
 // ------------------------------------------------------------------------------------------------
+// Sum of base[b*stride], b = 0 .. count-1, in index order, with 16 loads in flight per thread: the last-CTA reductions below are
+// chains of L2 round trips (one thread owns one output element), so their time is count / (loads in flight) x the L2 latency.
+__device__ __forceinline__ double ordered_sum_strided(const double* base, int count, int64_t stride) {
+    double s = 0.0;
+    int b = 0;
+    for (; b + 16 <= count; b += 16) {
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = __ldcg(base + (int64_t)(b + u) * stride);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) s += v[u];
+    }
+#pragma unroll 4
+    for (; b < count; ++b) s += __ldcg(base + (int64_t)b * stride);
+    return s;
+}
+
 constexpr int GRAM_ROWS_PER_CTA = 256;
 __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q, const double* __restrict__ A, int64_t lda,
                                                         const double* __restrict__ B, int64_t ldb, double* __restrict__ C, int64_t ldc,
@@ -204,10 +221,7 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q,
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    double s = 0.0;
-    const double* base = part + (int64_t)slot * nblk * 256 + threadIdx.x;
-#pragma unroll 8
-    for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * 256);   // loads batched, additions in block order
+    const double s = ordered_sum_strided(part + (int64_t)slot * nblk * 256 + threadIdx.x, nblk, 256);   // block order
     const int i = threadIdx.x % 16, j = threadIdx.x / 16;
     if (a0 + i < p && b0 + j < q) {
         double* dst = C + (a0 + i) + (int64_t)(b0 + j) * ldc;
@@ -281,10 +295,7 @@ __global__ void __launch_bounds__(256) gram_core_kernel(int64_t n, int r, const 
     sM[i][j] = in ? M[i + (int64_t)j * ld] : 0.0;
     sS[i][j] = in ? S0[i + (int64_t)j * ld] : 0.0;
     sN[i][j] = in ? Nn[i + (int64_t)j * ld] : 0.0;
-    double s = 0.0;
-    const double* base = part + threadIdx.x;
-#pragma unroll 8
-    for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * 256);   // fixed block order, as gram_dmma_kernel
+    double s = ordered_sum_strided(part + threadIdx.x, nblk, 256);   // fixed block order, as gram_dmma_kernel
     s = 0.0 + 1.0 * s;
     if (in) Rm[i + (int64_t)j * ld] = s;
     __syncthreads();
@@ -428,9 +439,7 @@ __global__ void __launch_bounds__(256, 1) gram_tile_kernel(int64_t n, int p, int
     for (int e = threadIdx.x; e < PART; e += 256) {
         const int i = e % GT_BLK, j = e / GT_BLK;
         if (a0 + i >= p || b0 + j >= q) continue;
-        double s = 0.0;
-#pragma unroll 8
-        for (int b = 0; b < nblk; ++b) s += __ldcg(base + (int64_t)b * PART + e);
+        const double s = ordered_sum_strided(base + e, nblk, PART);
         double* dst = C + (a0 + i) + (int64_t)(b0 + j) * ldc;
         *dst = (beta == 0.0 ? 0.0 : beta * (*dst)) + alpha * s;
     }
