@@ -69,6 +69,7 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_rnew, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_kqr, cudaEventDisableTiming));
+        DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_pass, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
         const int64_t W = e->W;
         auto dmalloc = [&](int64_t doubles) {
@@ -145,6 +146,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     if (h->ev_join) cudaEventDestroy(h->ev_join);
     if (h->ev_rnew) cudaEventDestroy(h->ev_rnew);
     if (h->ev_kqr) cudaEventDestroy(h->ev_kqr);
+    if (h->ev_pass) cudaEventDestroy(h->ev_pass);
     if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     h->UC.release();
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
@@ -476,6 +478,18 @@ static void qr_mside(dlra_handle h, Side sd, double* A, int C, double* R, int or
     ensure_qr_ws(sd, h->m, C);
     thin_qr(*sd.cx, h->self, h->m, C, A, h->m, A, h->m, R, h->W, sd.tws->p, sd.gws->p, sd.wtmp->p, ortho_cols);
 }
+// thin QR of (A + Va*Sa') in place on the m-side; the rank-k update rides on the panel load of the first TSQR level when it can
+static void qr_mside_plus(dlra_handle h, Side sd, double* A, int C, const double* Va, const double* Sa, int k) {
+    NvtxRange nvtx_qr("dlra:qr_mside_plus");
+    if (C <= TSQR_MAXC && h->m > 128) {
+        ensure_qr_ws(sd, h->m, C);
+        TsqrAdd add; add.U = Va; add.ldu = h->m; add.S = Sa; add.lds = h->W; add.k = k; add.transS = true;
+        tsqr(*sd.cx, h->self, h->m, C, A, h->m, A, h->m, nullptr, h->W, sd.tws->p, add);
+    } else {
+        gemm_nn(*sd.cx, h->m, k, C, Va, h->m, nullptr, 0, Sa, h->W, true, A, h->m, 1.0, 1.0);
+        qr_mside(h, sd, A, C, nullptr);
+    }
+}
 // p x q small matrix with ld W, summed over the row shards in place
 static void allreduce_small(dlra_handle h, double* C, int p, int q) {
     if (h->comm.nranks <= 1) return;
@@ -528,16 +542,18 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     double *K = h->UB, *L = h->VB;
     // K = U0*S0 (+ ΔA*V0);  L = V0*S0' (+ ΔA'*U0)   — one fused read of ΔA
     const bool pre = sc.is_data && h->kl_ready && h->kl_rank == r;   // formed by the previous step's pipelined pass
+    const bool lsum_done = pre && h->kl_lsum_done;                  // ... whose L partials were already summed into VB
     h->kl_ready = false;
+    h->kl_lsum_done = false;
     phase_mark(h, "step");
     // Single GPU: the whole L-side chain runs beside the K-side chain.  Row-sharded runs keep the cross-rank sum of L on the main
     // stream: measured at N = 2 (profiles/r02/multi_gpu_phases.txt) the spinning exchange kernel on the auxiliary stream competes
     // with the K-side TSQR for SMs and sets up a ~120 us ping-pong of arrival skew between the ranks (DLRA_LFIN_AUX=1 re-enables it).
     static const bool lfin_aux_multi = getenv("DLRA_LFIN_AUX") != nullptr;
-    const bool lfin_aux = pre && (h->comm.nranks <= 1 || (h->comm.p2p && lfin_aux_multi));
+    const bool lfin_aux = pre && !lsum_done && (h->comm.nranks <= 1 || (h->comm.p2p && lfin_aux_multi));
     if (pre) {
         // K = ΔA*V0 (already in UB) + U0*S0: the update is folded into the TSQR panel load below
-        if (!lfin_aux)
+        if (!lfin_aux && !lsum_done)
             l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, 16, 1, h->V, m, h->S, W, r, L, m);  // L = ΔA'*U0 + V0*S0'
     } else {
         gemm_nn(cx, n, r, r, h->U, n, nullptr, 0, h->S, W, false, K, n, 1.0, 0.0);
@@ -559,7 +575,8 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     const bool m_aux = pipe && gram_m_aux && h->comm.nranks <= 1;
     fork_aux(h);                                          // m-side chain on the auxiliary stream ...
     if (lfin_aux) l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, 16, 1, h->V, m, h->S, W, r, L, m, &h->ax);
-    qr_mside(h, aux_side(h), L, r, nullptr);              // V1 = qr(L).Q
+    if (lsum_done) qr_mside_plus(h, aux_side(h), L, r, h->V, h->S, r);   // V1 = qr(ΔA'*U0 + V0*S0').Q, the update folded into the panel load
+    else qr_mside(h, aux_side(h), L, r, nullptr);         // V1 = qr(L).Q
     gram_mside(h, aux_side(h), r, r, L, h->V, h->N);      // N = V1'*V0
     if (m_aux) DLRA_CUDA(cudaEventRecord(h->ev_join, h->ax.stream));   // the m-side is complete here
     if (pre) qr_nside_plus(h, K, r, h->U, h->S, r);       // ... overlaps U1 = qr(ΔA*V0 + U0*S0).Q
@@ -593,10 +610,20 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
             double* Knext = m_aux ? h->UC.p : h->U;   // the next step's K: third buffer, or the (no longer needed) buffer of U0
             tri_pass_launch(h, h->nxt, h->ldnxt, sc.d.A, sc.d.lda, sc.d.Aprev, sc.d.ldap, r, L, m, K, n, h->nscr.p, n,
                             Knext, n, h->part.p, ldlp, nsub, npanels);
+            static const bool lsum_early = !(getenv("DLRA_LSUM_EARLY") && atoi(getenv("DLRA_LSUM_EARLY")) == 0);
+            if (m_aux && lsum_early && m > 128) {
+                // the next step's L = sum of the per-CTA partials (+ V1*S1', folded into its QR): the sum does not need S1, so it runs on
+                // the auxiliary stream beside the core update instead of in front of the next step's m-side QR.  Target: the buffer of
+                // V0 (dead once N = V1'V0 exists; it is the next step's L buffer after the swap below).
+                DLRA_CUDA(cudaEventRecord(h->ev_pass, cx.stream));
+                DLRA_CUDA(cudaStreamWaitEvent(h->ax.stream, h->ev_pass, 0));
+                l_finalize(h, r, nparts, h->part.p, ldlp, 16, 1, nullptr, 0, nullptr, 0, r, h->V, m, &h->ax);
+                h->kl_lsum_done = true;
+            }
             if (m_aux) DLRA_CUDA(cudaStreamWaitEvent(cx.stream, h->ev_join2, 0));   // M is needed from here on
-            h->gws.ensure(gemm_tn_ws(cx, n, r, r), cx.stream);
+            h->gws.ensure(std::max(gemm_tn_ws(cx, n, r, r), gram_core_ws(n)), cx.stream);
             static const bool fused_core = !(getenv("DLRA_FUSED_CORE") && atoi(getenv("DLRA_FUSED_CORE")) == 0);
-            if (fused_core && h->comm.nranks <= 1 && r <= 16 && cx.counters) {
+            if (fused_core && h->comm.nranks <= 1 && r <= 16 && cx.counters && gram_core_ok(n)) {
                 // Rm = U1'*W and S1 = M*S0*N' + Rm in one launch (same arithmetic as the two kernels below)
                 h->kl_ready = true; h->kl_nparts = nparts; h->kl_ldlp = ldlp; h->kl_rank = r;
                 gram_core(cx, n, r, K, n, h->nscr.p, n, h->Rm, h->gws.p, h->M, h->S, h->N, h->S, (int)W);

@@ -110,6 +110,8 @@ struct dlra_engine {
     int own_next = 0; int cur_own = -1; int prev_own = -1; int nxt_own = -1;
     // software pipelining of the BUG step (pass_tri.cuh): ΔA·V0 already sits in UB and the per-CTA partials of ΔAᵀ·U0 in `part`
     bool kl_ready = false; int kl_nparts = 0; int64_t kl_ldlp = 0; int kl_rank = 0;
+    bool kl_lsum_done = false;   // ... and the fixed-order sum of those partials already sits in VB (formed beside the core update)
+    cudaEvent_t ev_pass = nullptr;
 
     // asynchronous factor snapshots (dlra_save_factors_async): two device staging slots, D2H on the copy stream
     dlra::DevBuf save_stage[2];

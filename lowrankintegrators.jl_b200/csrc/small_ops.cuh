@@ -234,11 +234,16 @@ __global__ void __launch_bounds__(256) gram_dmma_kernel(int64_t n, int p, int q,
 // arithmetic of gram_dmma_kernel, and — in the last CTA to finish — the core update  Out = M·S0·N' + Rm  with the arithmetic of
 // core_update_kernel (unconventional.jl:154-155).  Saves a launch and the round trip of Rm through global memory on the critical path
 // between the streaming pass and the next step's QR.  Out may alias S0.
+constexpr int GRAM_CORE_GROUP = 16;
+// scratch (doubles) and the largest row count the group counters (255 of the 256 per stream) allow
+inline int64_t gram_core_ws(int64_t n) { const int64_t nb = cdiv(n, GRAM_ROWS_PER_CTA); return (nb + cdiv(nb, GRAM_CORE_GROUP)) * 256; }
+inline bool gram_core_ok(int64_t n) { return cdiv(cdiv(n, GRAM_ROWS_PER_CTA), GRAM_CORE_GROUP) <= 255; }
 __global__ void __launch_bounds__(256) gram_core_kernel(int64_t n, int r, const double* __restrict__ A, int64_t lda,
                                                         const double* __restrict__ B, int64_t ldb, double* __restrict__ Rm,
                                                         double* __restrict__ part, unsigned int* __restrict__ counters,
                                                         const double* __restrict__ M, const double* S0,
                                                         const double* __restrict__ Nn, double* Out, int ld) {
+    constexpr int GC = GRAM_CORE_GROUP;
     __shared__ double red[8][256];
     __shared__ bool is_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, k = lane & 3;
@@ -276,11 +281,30 @@ __global__ void __launch_bounds__(256) gram_core_kernel(int64_t n, int r, const 
         for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
         part[(int64_t)blockIdx.x * 256 + threadIdx.x] = s;
     }
+    // Two-level fixed-order reduction (a single CTA summing all nblk partials is a chain of nblk/16 L2 round trips): the last CTA of
+    // every group of GC consecutive CTAs sums its group (one batch of loads), the last group to finish sums the group sums.
+    // counters[0]: finished groups; counters[1 + g]: finished CTAs of group g (all self-resetting).  The summation tree depends on
+    // the CTA indices only, never on the order of arrival.
+    const int ngrp = (nblk + GC - 1) / GC;
+    const int grp = blockIdx.x / GC;
+    const int gsize = min(GC, nblk - grp * GC);
+    double* gpart = part + (int64_t)nblk * 256;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int ticket = atomicAdd(&counters[1 + grp], 1u);
+        is_last = (ticket == (unsigned int)gsize - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    gpart[(int64_t)grp * 256 + threadIdx.x] = ordered_sum_strided(part + (int64_t)grp * GC * 256 + threadIdx.x, gsize, 256);
+    if (threadIdx.x == 0) counters[1 + grp] = 0;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int ticket = atomicAdd(&counters[0], 1u);
-        is_last = (ticket == (unsigned int)nblk - 1);
+        is_last = (ticket == (unsigned int)ngrp - 1);
     }
     __syncthreads();
     if (!is_last) return;
@@ -295,7 +319,7 @@ __global__ void __launch_bounds__(256) gram_core_kernel(int64_t n, int r, const 
     sM[i][j] = in ? M[i + (int64_t)j * ld] : 0.0;
     sS[i][j] = in ? S0[i + (int64_t)j * ld] : 0.0;
     sN[i][j] = in ? Nn[i + (int64_t)j * ld] : 0.0;
-    double s = ordered_sum_strided(part + threadIdx.x, nblk, 256);   // fixed block order, as gram_dmma_kernel
+    double s = ordered_sum_strided(gpart + threadIdx.x, ngrp, 256);   // fixed group order
     s = 0.0 + 1.0 * s;
     if (in) Rm[i + (int64_t)j * ld] = s;
     __syncthreads();

@@ -219,8 +219,9 @@ __device__ __noinline__ void tsqr_level1(double* stack, double* stack2, double* 
 // unconventional.jl:137, folded into the factorisation so K is not re-read and re-written by a separate GEMM)
 struct TsqrAdd {
     const double* U = nullptr; int64_t ldu = 0;   // rows x k
-    const double* S = nullptr; int64_t lds = 0;   // k x C
+    const double* S = nullptr; int64_t lds = 0;   // k x C  (transS: stored C x k, i.e. the update is Ua*S')
     int k = 0;
+    bool transS = false;
 };
 
 template <int CP>
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_reg_kernel(int64_t rows,
             // stage Sa (k x C) in the (still unused) stack area, then a[q][:] += Ua[row, :] * Sa
             for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) {
                 const int kk = e / CP, c = e % CP;
-                stack[e] = (kk < add.k && c < C) ? add.S[kk + (int64_t)c * add.lds] : 0.0;
+                stack[e] = (kk < add.k && c < C) ? (add.transS ? add.S[c + (int64_t)kk * add.lds] : add.S[kk + (int64_t)c * add.lds]) : 0.0;
             }
             __syncthreads();
 #pragma unroll 1
@@ -495,7 +496,7 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_cta_kernel(int64_t rows,
     if (add.U) {
         for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) {
             const int kk = e / CP, c = e % CP;
-            sadd[e] = (kk < add.k && c < C) ? add.S[kk + (int64_t)c * add.lds] : 0.0;
+            sadd[e] = (kk < add.k && c < C) ? (add.transS ? add.S[c + (int64_t)kk * add.lds] : add.S[kk + (int64_t)c * add.lds]) : 0.0;
         }
         __syncthreads();
 #pragma unroll 1
