@@ -569,10 +569,12 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     phase_mark(h, "KL_or_Lsum");
     const bool pipe = sc.is_data && !(h->flags & DLRA_FORCE_GENERIC) && h->have_nxt && h->nxt_kind == DLRA_DATA_SNAPSHOT &&
                       sc.d.Aprev != nullptr && r <= 16 && tma_pass_supported(n, m, sc.d) && tma_ok(h->nxt, h->ldnxt);
-    // Single GPU, pipelined pass: M = U1'*U0 leaves the critical path.  It runs on the auxiliary stream BESIDE the streaming pass
-    // (which then writes the next step's K into a third buffer instead of the buffer of U0) and is only needed by the core update.
+    // Pipelined pass: M = U1'*U0 (local rows) leaves the critical path.  It runs on the auxiliary stream BESIDE the streaming pass
+    // (which then writes the next step's K into a third buffer instead of the buffer of U0) and is only needed by the core update /
+    // the M + core all-reduce after the pass.  No exchange runs on the auxiliary stream because of it.
     static const bool gram_m_aux = !(getenv("DLRA_GRAM_M_AUX") && atoi(getenv("DLRA_GRAM_M_AUX")) == 0);
-    const bool m_aux = pipe && gram_m_aux && h->comm.nranks <= 1;
+    static const bool gram_m_aux_multi = !(getenv("DLRA_GRAM_M_AUX_MULTI") && atoi(getenv("DLRA_GRAM_M_AUX_MULTI")) == 0);
+    const bool m_aux = pipe && gram_m_aux && (h->comm.nranks <= 1 || gram_m_aux_multi);
     fork_aux(h);                                          // m-side chain on the auxiliary stream ...
     if (lfin_aux) l_finalize(h, r, h->kl_nparts, h->part.p, h->kl_ldlp, 16, 1, h->V, m, h->S, W, r, L, m, &h->ax);
     if (lsum_done) qr_mside_plus(h, aux_side(h), L, r, h->V, h->S, r);   // V1 = qr(ΔA'*U0 + V0*S0').Q, the update folded into the panel load
@@ -611,7 +613,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
             tri_pass_launch(h, h->nxt, h->ldnxt, sc.d.A, sc.d.lda, sc.d.Aprev, sc.d.ldap, r, L, m, K, n, h->nscr.p, n,
                             Knext, n, h->part.p, ldlp, nsub, npanels);
             static const bool lsum_early = !(getenv("DLRA_LSUM_EARLY") && atoi(getenv("DLRA_LSUM_EARLY")) == 0);
-            if (m_aux && lsum_early && m > 128) {
+            if (m_aux && lsum_early && m > 128 && h->comm.nranks <= 1) {
                 // the next step's L = sum of the per-CTA partials (+ V1*S1', folded into its QR): the sum does not need S1, so it runs on
                 // the auxiliary stream beside the core update instead of in front of the next step's m-side QR.  Target: the buffer of
                 // V0 (dead once N = V1'V0 exists; it is the next step's L buffer after the swap below).
