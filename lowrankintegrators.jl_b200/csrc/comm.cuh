@@ -47,6 +47,7 @@ __device__ __forceinline__ double ld_relaxed_sys(const double* p) {
 struct LLView {
     int nranks, rank;
     unsigned int seq;            // never 0 (the buffers start zeroed)
+    int fence;                   // 1: membar.sys after the pushes of a kernel (see ll_flush)
     int64_t cap;                 // elements per sender slot
     uint4* local;                // this rank's buffer of the current parity: [nranks][cap]
     uint4* peer[P2P_MAX_RANKS];  // the same buffer in every rank (own included)
@@ -62,6 +63,12 @@ __device__ __forceinline__ double ll_load(const uint4* p, unsigned int seq) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
     } while (f1 != seq || f2 != seq);
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
+// After the last push of a kernel: nothing orders a posted remote store against the spin loop that follows it, so the hardware may
+// keep the tail of the pushes in flight until the kernel retires.  With DLRA_LL_FENCE=1 every pushing thread drains its own stores
+// (membar.sys: one NVLink round trip) before it starts to poll.  A/B in profiles/r02/multi_gpu_r02b.txt.
+__device__ __forceinline__ void ll_flush(const LLView& v) {
+    if (v.fence) __threadfence_system();
 }
 // one attempt (no spinning): many of these can be in flight before the first flag is inspected
 __device__ __forceinline__ bool ll_try_load(const uint4* p, unsigned int seq, double& out) {
@@ -84,12 +91,14 @@ __device__ __forceinline__ double ll_sum(const LLView& v, int64_t e) {
 __global__ void __launch_bounds__(256) ll_allreduce_kernel(LLView v, double* __restrict__ buf, int64_t count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) ll_push(v, e, buf[e]);
+    ll_flush(v);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) buf[e] = ll_sum(v, e);
 }
 // dst[g*count + i] = rank g's src[i]
 __global__ void __launch_bounds__(256) ll_allgather_kernel(LLView v, const double* __restrict__ src, double* __restrict__ dst, int64_t count) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) ll_push(v, e, src[e]);
+    ll_flush(v);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count * v.nranks; e += stride) {
         const int g = (int)(e / count);
         dst[e] = ll_load(v.local + (size_t)g * v.cap + (e - (int64_t)g * count), v.seq);
@@ -176,6 +185,7 @@ __global__ void __launch_bounds__(256) ll_small_allreduce_kernel(LLView v, Small
             ll_push(v, off + e, sm.p[q][(e % sm.rows[q]) + (int64_t)(e / sm.rows[q]) * sm.ld[q]]);
         off += cnt;
     }
+    ll_flush(v);
     off = 0;
     for (int q = 0; q < sm.n; ++q) {
         const int cnt = sm.rows[q] * sm.cols[q];
@@ -196,6 +206,7 @@ __global__ void __launch_bounds__(256) ll_allreduce_core_kernel(LLView v, int r,
         ll_push(v, threadIdx.x, M[i + (int64_t)j * ld]);
         ll_push(v, 256 + threadIdx.x, R[i + (int64_t)j * ld]);
     }
+    ll_flush(v);
     const double ms = in ? ll_sum(v, threadIdx.x) : 0.0;
     const double rs = in ? ll_sum(v, 256 + threadIdx.x) : 0.0;
     if (in) { M[i + (int64_t)j * ld] = ms; R[i + (int64_t)j * ld] = rs; }
@@ -297,7 +308,8 @@ struct Comm {
         const size_t par = (size_t)(sq & 1);
         const size_t base = NCHAN * chan_bytes() + (size_t)chan * ll_chan_bytes() + par * (size_t)P2P_MAX_RANKS * (size_t)ll_cap * 16;
         LLView v;
-        v.nranks = nranks; v.rank = rank; v.seq = sq; v.cap = ll_cap;
+        static const int fence = (getenv("DLRA_LL_FENCE") && atoi(getenv("DLRA_LL_FENCE")) != 0) ? 1 : 0;
+        v.nranks = nranks; v.rank = rank; v.seq = sq; v.cap = ll_cap; v.fence = fence;
         v.local = (uint4*)(xbuf + base);
         for (int g = 0; g < P2P_MAX_RANKS; ++g) v.peer[g] = (uint4*)((xpeer[g] ? xpeer[g] : xbuf) + base);
         return v;

@@ -552,6 +552,7 @@ __global__ void __launch_bounds__(256) l_finalize_kernel(int64_t m, int rc, int 
     }
     if (XR == 0) return;
     if (XR == 2) {
+        ll_flush(lv);
         for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gstride) {
             const int64_t j = e % m;
             const int c = (int)(e / m);

@@ -575,6 +575,7 @@ __global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, LLView lv,
     const int nranks = LL ? lv.nranks : v.nranks, rank = LL ? lv.rank : v.rank;
     if (LL) {
         for (int e = lane; e < CP * CP; e += 32) ll_push(lv, e, Rloc[e]);   // flag-in-data: R goes straight into every rank's buffer
+        ll_flush(lv);
     } else {
         for (int e = lane; e < CP * CP; e += 32) v.data_local[e] = Rloc[e];
         __syncwarp();
