@@ -373,6 +373,9 @@ def step(integ: DLRIntegrator, alg=None, dt=None):
     if isinstance(alg, ProjectorSplitting):
         if isinstance(alg.order, Strang):
             if is_data:  # each half fetches its own increment (projector_splitting.jl:205-211)
+                if integ._pushed > 0:
+                    raise RuntimeError("a previous unconventional step with lookahead already handed y(t + dt) to the engine; the Strang "
+                                       "step needs y(t + dt/2) next: use init(..., lookahead=False) when mixing these integrators")
                 eng.data_push(_fetch(y, t, dt / 2))
                 eng.step_ksl(L.KSL_PRIMAL, t, dt / 2)
                 eng.data_push(_fetch(y, t + dt / 2, dt / 2))

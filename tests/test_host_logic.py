@@ -201,3 +201,12 @@ def test_switching_algorithms_after_a_lookahead_step_pushes_each_snapshot_once(f
     assert pushes == [1.0, 2.0, 3.0]
     kinds = [c[0] for c in fake.log[0].calls if c[0] in ("bug", "ksl", "rabug")]
     assert kinds == ["bug", "ksl", "rabug"]
+
+
+def test_strang_step_after_a_lookahead_step_is_refused(fake):
+    # the queued snapshot is y(t + dt), the Strang step needs y(t + dt/2) first: refuse instead of silently feeding the wrong increment
+    y = lambda t: np.full((6, 5), float(t))
+    integ = lri.init(lri.MatrixDataProblem(y, _u0(), tspan=(0.0, 4.0)), lri.UnconventionalAlgorithm(), 1.0)
+    lri.step(integ)
+    with pytest.raises(RuntimeError, match="lookahead"):
+        lri.step(integ, lri.ProjectorSplitting(lri.Strang()))
