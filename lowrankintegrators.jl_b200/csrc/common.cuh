@@ -60,6 +60,9 @@ struct Ctx {
     int64_t launches = 0;
     int num_sms = 148;
     unsigned int* counters = nullptr;   // zero-initialised device counters for last-block-done reductions (self-resetting)
+    // one-launch TSQR (tsqr_fused_kernel): [0] R factors published (running total), [1] epoch of the finished tree top, [2] time-outs
+    unsigned int* sync = nullptr;
+    unsigned int sync_arrivals = 0, sync_epoch = 0;   // host copies of the running totals (wrap-around arithmetic)
     // main stream only: tall products n x p times p x q go through the TMA/DMMA streaming kernels when they fit (pass_tma.cuh)
     bool (*tall_gemm)(void* eng, int64_t n, int p, int q, const double* A, int64_t lda, const double* B, int64_t ldb, bool transB,
                       double* C, int64_t ldc, double alpha, double beta) = nullptr;

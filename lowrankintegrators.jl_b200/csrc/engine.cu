@@ -86,9 +86,11 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         e->S = sb; sb += W * W; e->M = sb; sb += W * W; e->N = sb; sb += W * W; e->Sh = sb; sb += W * W;
         e->T1 = sb; sb += W * W; e->T2 = sb; sb += W * W; e->Rm = sb; sb += W * W; e->Pm = sb; sb += W * W;
         e->Qm = sb; sb += W * W; e->stg = sb; sb += 8 * W * W; e->sig = sb; sb += W; e->scal_dev = sb + W;
-        DLRA_CUDA(cudaMalloc(&e->cx.counters, 512 * sizeof(unsigned int)));
-        DLRA_CUDA(cudaMemsetAsync(e->cx.counters, 0, 512 * sizeof(unsigned int), e->cx.stream));
+        DLRA_CUDA(cudaMalloc(&e->cx.counters, (512 + 16) * sizeof(unsigned int)));
+        DLRA_CUDA(cudaMemsetAsync(e->cx.counters, 0, (512 + 16) * sizeof(unsigned int), e->cx.stream));
         e->ax.counters = e->cx.counters + 256;
+        e->cx.sync = e->cx.counters + 512;
+        e->ax.sync = e->cx.counters + 520;
         DLRA_CUDA(cudaMalloc(&e->r_new_dev, sizeof(int)));
         DLRA_CUDA(cudaHostAlloc(&e->r_new_host, sizeof(int), cudaHostAllocDefault));
         *e->r_new_host = r0;

@@ -528,6 +528,188 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_cta_kernel(int64_t rows,
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Two-level TSQR in ONE launch (2 <= nb <= 64 row blocks of 1024, i.e. up to 65536 rows per GPU — the headline shape).
+// CTAs 0 .. nb-1 factor their panel (cta_panel_qr), publish R, and form their explicit Q block while CTA nb — which only waits
+// for the R factors — factors the stacked R's and forms the top Q; the panel CTAs then multiply their register-resident Q block by
+// their CP x CP block of the top Q and write the result once.  Against the three launches (level 0, level 1, apply_blocks) the
+// sequential chain loses the explicit-Q recurrence of level 0 (it overlaps level 1), the apply launch and one round trip of Q
+// through memory.  Arithmetic and summation orders are those of the three kernels (bit-identical results).
+// All nb + 1 CTAs must be co-resident while they wait for each other: one CTA per SM, nb + 1 <= 65 of 148 SMs, and nothing that
+// runs beside this kernel (auxiliary-stream kernels, the single-GPU exchange-free tail) blocks an SM forever.  The waits are
+// bounded (a few seconds) and report a time-out in sync[2] instead of hanging the device.
+// sync[0]: running total of published R factors; sync[1]: epoch of the last finished top factorisation.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// thread 0 of the CTA waits until *p has reached `target` (wrap-around compare), then releases the CTA
+__device__ __forceinline__ void cta_wait_reached(unsigned int* p, unsigned int target, unsigned int* timeouts) {
+    if (threadIdx.x == 0) {
+        long long spins = 0;
+        while ((int)(ld_acquire_gpu_u32(p) - target) < 0) {
+            __nanosleep(64);
+            if (++spins > (1ll << 25)) { atomicAdd(timeouts, 1u); break; }
+        }
+    }
+    __syncthreads();
+}
+
+template <int CP>
+__global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_fused_kernel(int64_t rows, int C, int nb, const double* __restrict__ A, int64_t lda,
+                                                                    double* __restrict__ Q, int64_t ldq, double* __restrict__ Rstack,
+                                                                    double* __restrict__ Qtop, double* __restrict__ Rtop, TsqrAdd add,
+                                                                    unsigned int* sync, unsigned int arrivals_target, unsigned int epoch) {
+    using SM = TsqrCtaSmem<CP>;
+    constexpr int RPL0 = TSQR_RPL0;
+    constexpr int PROWS = SM::PROWS;
+    constexpr int VLD = TSQR_NW * PROWS;
+    extern __shared__ __align__(16) double tsm[];
+    double* park = tsm;                                   // [CP][VLD]
+    double* part = park + SM::PARK;                       // [2][NW][CP]
+    double* prow = part + 2 * TSQR_NW * CP;               // [2][CP]
+    double* taus = prow + 2 * CP;                         // [CP]
+    double* bcast = taus + CP;                            // [NW][2*CP]
+    double* sadd = bcast + TSQR_NW * 2 * CP;              // [CP][CP]: staged Sa of the fused rank-k update, later this CTA's block of the top Q
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* bc = bcast + warp * 2 * CP;
+    double* mypark = park + warp * PROWS;
+    const int64_t ldr = (int64_t)nb * CP;                 // leading dimension of Rstack and Qtop
+    double a[RPL0][CP];
+
+    if ((int)blockIdx.x == nb) {
+        // ---- top of the tree: wait for the nb R factors, factor the (nb*CP) x CP stack, publish R and the explicit top Q
+        cta_wait_reached(sync + 0, arrivals_target, sync + 2);
+        const int srows = nb * CP;
+        if (srows <= 128) {
+            // small stack: one warp, register panel of 128 rows (the arithmetic of tsqr_small_kernel)
+            if (warp == 0) {
+#pragma unroll
+                for (int c = 0; c < CP; ++c)
+#pragma unroll
+                    for (int q = 0; q < RPL0; ++q) {
+                        const int g = lane + 32 * q;
+                        a[q][c] = (g < srows) ? __ldcg(Rstack + g + (int64_t)c * ldr) : 0.0;
+                    }
+                reg_panel_qr<CP, RPL0>(a, park, 32 * RPL0, taus, lane, bc);
+                if (lane < CP) {
+#pragma unroll
+                    for (int c = 0; c < CP; ++c) Rtop[lane + (int64_t)c * CP] = (lane <= c) ? park[c * (32 * RPL0) + lane] : 0.0;
+                }
+                reg_panel_formq<CP, RPL0>(a, park, 32 * RPL0, taus, lane, bc);
+#pragma unroll
+                for (int c = 0; c < CP; ++c)
+#pragma unroll
+                    for (int q = 0; q < RPL0; ++q) {
+                        const int g = lane + 32 * q;
+                        if (g < srows) Qtop[g + (int64_t)c * ldr] = a[q][c];
+                    }
+            }
+        } else {
+            const int r0 = warp * PROWS + lane;
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+#pragma unroll
+                for (int q = 0; q < RPL0; ++q) {
+                    const int g = r0 + 32 * q;
+                    a[q][c] = (g < srows) ? __ldcg(Rstack + g + (int64_t)c * ldr) : 0.0;
+                }
+            cta_panel_qr<CP, RPL0, TSQR_NW>(a, mypark, VLD, taus, warp, lane, bc, part, prow);
+            if (warp == 0 && lane < CP) {
+#pragma unroll
+                for (int c = 0; c < CP; ++c) Rtop[lane + (int64_t)c * CP] = (lane <= c) ? park[c * VLD + lane] : 0.0;
+            }
+            cta_panel_formq<CP, RPL0, TSQR_NW>(a, mypark, VLD, taus, warp, lane, bc, part);
+#pragma unroll
+            for (int c = 0; c < CP; ++c)
+#pragma unroll
+                for (int q = 0; q < RPL0; ++q) {
+                    const int g = r0 + 32 * q;
+                    if (g < srows) Qtop[g + (int64_t)c * ldr] = a[q][c];
+                }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { __threadfence(); st_release_gpu_u32(sync + 1, epoch); }
+        return;
+    }
+
+    // ---- panel CTA: rows [1024 b, 1024 b + 1024)
+    const int64_t row0 = (int64_t)blockIdx.x * TSQR_BR + warp * PROWS;
+    bool ok[RPL0];
+#pragma unroll
+    for (int q = 0; q < RPL0; ++q) ok[q] = (row0 + lane + 32 * q) < rows;
+    {
+        const double* col = A + row0 + lane;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+#pragma unroll
+            for (int q = 0; q < RPL0; ++q) a[q][c] = (ok[q] && c < C) ? col[32 * q] : 0.0;
+            col += lda;
+        }
+    }
+    if (add.U) {
+        for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) {
+            const int kk = e / CP, c = e % CP;
+            sadd[e] = (kk < add.k && c < C) ? (add.transS ? add.S[c + (int64_t)kk * add.lds] : add.S[kk + (int64_t)c * add.lds]) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int kk = 0; kk < add.k; ++kk) {
+            double u[RPL0];
+#pragma unroll
+            for (int q = 0; q < RPL0; ++q) u[q] = ok[q] ? add.U[row0 + lane + 32 * q + (int64_t)kk * add.ldu] : 0.0;
+#pragma unroll
+            for (int c = 0; c < CP; ++c) {
+                const double sv = sadd[kk * CP + c];
+#pragma unroll
+                for (int q = 0; q < RPL0; ++q) a[q][c] = fma(u[q], sv, a[q][c]);
+            }
+        }
+    }
+    cta_panel_qr<CP, RPL0, TSQR_NW>(a, mypark, VLD, taus, warp, lane, bc, part, prow);
+    if (warp == 0 && lane < CP) {
+#pragma unroll
+        for (int c = 0; c < CP; ++c) Rstack[(int64_t)blockIdx.x * CP + lane + (int64_t)c * ldr] = (lane <= c) ? park[c * VLD + lane] : 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(sync + 0, 1u); }     // this panel's R is published
+    cta_panel_formq<CP, RPL0, TSQR_NW>(a, mypark, VLD, taus, warp, lane, bc, part);   // overlaps the top factorisation
+    // park the explicit Q block in shared memory (the Householder vectors there are dead; every thread rereads only its own
+    // entries): the register panel is free while this CTA waits and during the product below
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < CP; ++c)
+#pragma unroll
+        for (int q = 0; q < RPL0; ++q) mypark[c * VLD + lane + 32 * q] = a[q][c];
+    cta_wait_reached(sync + 1, epoch, sync + 2);
+    // this CTA's CP x CP block X_b of the top Q:  Q_block <- Q_block * X_b  (the arithmetic of apply_blocks_kernel)
+    for (int e = threadIdx.x; e < CP * CP; e += blockDim.x) {
+        const int k = e % CP, c = e / CP;
+        sadd[k * CP + c] = (k < C && c < C) ? __ldcg(Qtop + (int64_t)blockIdx.x * CP + k + (int64_t)c * ldr) : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int q = 0; q < RPL0; ++q) {
+        double x[CP];
+#pragma unroll
+        for (int k = 0; k < CP; ++k) x[k] = (k < C) ? mypark[k * VLD + lane + 32 * q] : 0.0;
+        double* qcol = Q + row0 + lane + 32 * q;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < CP; ++k) s = fma(x[k], sadd[k * CP + c], s);
+            if (ok[q] && c < C) *qcol = s;
+            qcol += ldq;
+        }
+    }
+}
+
 // rows <= 128: one warp factors the whole matrix (used for the top of the tree and for all-gathered R stacks)
 template <int CP>
 __global__ void __launch_bounds__(32, 1) tsqr_small_kernel(int rows, int C, const double* __restrict__ A, int64_t lda,
@@ -719,6 +901,22 @@ inline double* tsqr_local(Ctx& cx, int64_t rows, int C, const double* A, int64_t
     double* Rstack = ws;                    // (nb*CP) x CP, ld = nb*CP
     double* Qtop = ws + nb * CP * CP;       // same shape
     double* rest = Qtop + nb * CP * CP;
+    static const bool fused = !(getenv("DLRA_TSQR_FUSED") && atoi(getenv("DLRA_TSQR_FUSED")) == 0) && getenv("DLRA_TSQR_LEGACY") == nullptr;
+    if (fused && nb >= 2 && nb <= 64 && nb + 1 <= cx.num_sms / 2 && cx.sync != nullptr) {
+        static unsigned long long attr_devs_f = 0;
+        if (first_use_on_this_device(attr_devs_f)) {
+            DLRA_CUDA(cudaFuncSetAttribute(tsqr_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrCtaSmem<8>::BYTES));
+            DLRA_CUDA(cudaFuncSetAttribute(tsqr_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrCtaSmem<16>::BYTES));
+        }
+        cx.sync_arrivals += (unsigned int)nb;
+        cx.sync_epoch += 1;
+        double* Rtop = rest;                // CP x CP, ld = CP (where the recursion below would put it)
+        if (CP == 8) tsqr_fused_kernel<8><<<(unsigned)nb + 1, TSQR_NW * 32, TsqrCtaSmem<8>::BYTES, cx.stream>>>(rows, C, (int)nb, A, lda, Q, ldq, Rstack, Qtop, Rtop, add, cx.sync, cx.sync_arrivals, cx.sync_epoch);
+        else tsqr_fused_kernel<16><<<(unsigned)nb + 1, TSQR_NW * 32, TsqrCtaSmem<16>::BYTES, cx.stream>>>(rows, C, (int)nb, A, lda, Q, ldq, Rstack, Qtop, Rtop, add, cx.sync, cx.sync_arrivals, cx.sync_epoch);
+        cx.launches++;
+        DLRA_CUDA(cudaGetLastError());
+        return Rtop;
+    }
     tsqr_level(cx, CP, rows, C, A, lda, Q, ldq, Rstack, nb * CP, add);
     if (nb == 1) return Rstack;
     double* Rtop = tsqr_local(cx, nb * CP, CP, Rstack, nb * CP, Qtop, nb * CP, rest);
