@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_cta_kernel(int64_t rows,
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Two-level TSQR in ONE launch (2 <= nb <= 64 row blocks of 1024, i.e. up to 65536 rows per GPU — the headline shape).
+// Two-level TSQR in ONE launch (8 <= nb <= 64 row blocks of 1024, i.e. up to 65536 rows per GPU — the headline shape).
 // CTAs 0 .. nb-1 factor their panel (cta_panel_qr), publish R, and form their explicit Q block while CTA nb — which only waits
 // for the R factors — factors the stacked R's and forms the top Q; the panel CTAs then multiply their register-resident Q block by
 // their CP x CP block of the top Q and write the result once.  Against the three launches (level 0, level 1, apply_blocks) the
@@ -902,7 +902,10 @@ inline double* tsqr_local(Ctx& cx, int64_t rows, int C, const double* A, int64_t
     double* Qtop = ws + nb * CP * CP;       // same shape
     double* rest = Qtop + nb * CP * CP;
     static const bool fused = !(getenv("DLRA_TSQR_FUSED") && atoi(getenv("DLRA_TSQR_FUSED")) == 0) && getenv("DLRA_TSQR_LEGACY") == nullptr;
-    if (fused && nb >= 2 && nb <= 64 && nb + 1 <= cx.num_sms / 2 && cx.sync != nullptr) {
+    // measured (profiles/r02/tsqr_fused_ab.txt): 64 blocks 87.5 -> 78.0 us; with 4 blocks (m = 4096) the single launch is SLOWER than the
+    // three small ones (68 vs 57 us), so short trees keep the three-launch path
+    static const int fused_min_nb = getenv("DLRA_TSQR_FUSED_MIN") ? atoi(getenv("DLRA_TSQR_FUSED_MIN")) : 8;
+    if (fused && nb >= fused_min_nb && nb >= 2 && nb <= 64 && nb + 1 <= cx.num_sms / 2 && cx.sync != nullptr) {
         static unsigned long long attr_devs_f = 0;
         if (first_use_on_this_device(attr_devs_f)) {
             DLRA_CUDA(cudaFuncSetAttribute(tsqr_fused_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TsqrCtaSmem<8>::BYTES));
