@@ -48,6 +48,7 @@ struct LLView {
     int nranks, rank;
     unsigned int seq;            // never 0 (the buffers start zeroed)
     int fence;                   // 1: membar.sys after the pushes of a kernel (see ll_flush)
+    int backoff;                 // > 0: nanoseconds to sleep after a failed poll (a tight volatile-load loop on the lines a peer is writing)
     int64_t cap;                 // elements per sender slot
     uint4* local;                // this rank's buffer of the current parity: [nranks][cap]
     uint4* peer[P2P_MAX_RANKS];  // the same buffer in every rank (own included)
@@ -57,11 +58,13 @@ __device__ __forceinline__ void ll_store(uint4* p, double v, unsigned int seq) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)b), "r"(seq), "r"((unsigned int)(b >> 32)), "r"(seq)
                  : "memory");
 }
-__device__ __forceinline__ double ll_load(const uint4* p, unsigned int seq) {
+__device__ __forceinline__ double ll_load(const uint4* p, unsigned int seq, int backoff = 0) {
     unsigned int lo, f1, hi, f2;
-    do {
+    while (true) {
         asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
-    } while (f1 != seq || f2 != seq);
+        if (f1 == seq && f2 == seq) break;
+        if (backoff > 0) __nanosleep(backoff);
+    }
     return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
 }
 // After the last push of a kernel: nothing orders a posted remote store against the spin loop that follows it, so the hardware may
@@ -84,7 +87,7 @@ __device__ __forceinline__ void ll_push(const LLView& v, int64_t e, double val) 
 // sum over ranks of element e, in rank order (bit-identical on every rank)
 __device__ __forceinline__ double ll_sum(const LLView& v, int64_t e) {
     double s = 0.0;
-    for (int g = 0; g < v.nranks; ++g) s += ll_load(v.local + (size_t)g * v.cap + e, v.seq);
+    for (int g = 0; g < v.nranks; ++g) s += ll_load(v.local + (size_t)g * v.cap + e, v.seq, v.backoff);
     return s;
 }
 // in-place all-reduce of a dense vector: one launch, every thread pushes its elements and then collects the peers' copies
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(256) ll_allgather_kernel(LLView v, const doubl
     ll_flush(v);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count * v.nranks; e += stride) {
         const int g = (int)(e / count);
-        dst[e] = ll_load(v.local + (size_t)g * v.cap + (e - (int64_t)g * count), v.seq);
+        dst[e] = ll_load(v.local + (size_t)g * v.cap + (e - (int64_t)g * count), v.seq, v.backoff);
     }
 }
 
@@ -309,7 +312,8 @@ struct Comm {
         const size_t base = NCHAN * chan_bytes() + (size_t)chan * ll_chan_bytes() + par * (size_t)P2P_MAX_RANKS * (size_t)ll_cap * 16;
         LLView v;
         static const int fence = (getenv("DLRA_LL_FENCE") && atoi(getenv("DLRA_LL_FENCE")) != 0) ? 1 : 0;
-        v.nranks = nranks; v.rank = rank; v.seq = sq; v.cap = ll_cap; v.fence = fence;
+        static const int backoff = getenv("DLRA_LL_BACKOFF_NS") ? atoi(getenv("DLRA_LL_BACKOFF_NS")) : 0;
+        v.nranks = nranks; v.rank = rank; v.seq = sq; v.cap = ll_cap; v.fence = fence; v.backoff = backoff;
         v.local = (uint4*)(xbuf + base);
         for (int g = 0; g < P2P_MAX_RANKS; ++g) v.peer[g] = (uint4*)((xpeer[g] ? xpeer[g] : xbuf) + base);
         return v;

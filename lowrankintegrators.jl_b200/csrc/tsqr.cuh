@@ -785,6 +785,7 @@ __global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, LLView lv,
                     if (gr >= rows) a[q][c] = 0.0;
                     else ok &= ll_try_load(lv.local + (size_t)g * lv.cap + i + c * CP, lv.seq, a[q][c]);
                 }
+                if (!ok && lv.backoff > 0) __nanosleep(lv.backoff);
             } while (!ok);
         } else {
 #pragma unroll
