@@ -551,10 +551,11 @@ __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int
 // thread 0 of the CTA waits until *p has reached `target` (wrap-around compare), then releases the CTA
 __device__ __forceinline__ void cta_wait_reached(unsigned int* p, unsigned int target, unsigned int* timeouts) {
     if (threadIdx.x == 0) {
+        // plain spin of ONE thread (the others sit at the barrier): a nanosleep between the polls costs tens of microseconds per wait on
+        // this part (measured with the LL exchange, profiles/r02/multi_gpu_r02b.txt), far more than the poll traffic it saves
         long long spins = 0;
         while ((int)(ld_acquire_gpu_u32(p) - target) < 0) {
-            __nanosleep(64);
-            if (++spins > (1ll << 25)) { atomicAdd(timeouts, 1u); break; }
+            if (++spins > (1ll << 22)) { atomicAdd(timeouts, 1u); break; }   // a few seconds
         }
     }
     __syncthreads();
