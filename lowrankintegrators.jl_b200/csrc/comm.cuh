@@ -49,6 +49,7 @@ struct LLView {
     unsigned int seq;            // never 0 (the buffers start zeroed)
     int fence;                   // 1: membar.sys after the pushes of a kernel (see ll_flush)
     int backoff;                 // > 0: nanoseconds to sleep after a failed poll (a tight volatile-load loop on the lines a peer is writing)
+    int atomic_poll;             // 1: poll with a 128-bit compare-and-swap that never matches (served by the L2 slice that owns the line)
     int64_t cap;                 // elements per sender slot
     uint4* local;                // this rank's buffer of the current parity: [nranks][cap]
     uint4* peer[P2P_MAX_RANKS];  // the same buffer in every rank (own included)
@@ -58,10 +59,24 @@ __device__ __forceinline__ void ll_store(uint4* p, double v, unsigned int seq) {
     asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned int)b), "r"(seq), "r"((unsigned int)(b >> 32)), "r"(seq)
                  : "memory");
 }
-__device__ __forceinline__ double ll_load(const uint4* p, unsigned int seq, int backoff = 0) {
+// 16-byte read performed AT the point of coherence: a compare-and-swap whose compare value cannot occur (the two flag words differ)
+// and whose swap value equals it, so memory never changes.  Unlike a load it cannot be served from a copy of the line that some
+// cache level took before the peer's store arrived.
+__device__ __forceinline__ void ll_read_coherent(const uint4* p, unsigned int& lo, unsigned int& f1, unsigned int& hi, unsigned int& f2) {
+    unsigned long long a, b;
+    asm volatile(
+        "{\n\t.reg .b128 d, c;\n\t"
+        "mov.b128 c, {%3, %4};\n\t"
+        "atom.global.sys.relaxed.cas.b128 d, [%2], c, c;\n\t"
+        "mov.b128 {%0, %1}, d;\n\t}"
+        : "=l"(a), "=l"(b) : "l"(p), "l"(0xdeadbeef00000000ULL), "l"(0xfeedface00000000ULL) : "memory");
+    lo = (unsigned int)a; f1 = (unsigned int)(a >> 32); hi = (unsigned int)b; f2 = (unsigned int)(b >> 32);
+}
+__device__ __forceinline__ double ll_load(const uint4* p, unsigned int seq, int backoff = 0, int atomic_poll = 0) {
     unsigned int lo, f1, hi, f2;
     while (true) {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+        if (atomic_poll) ll_read_coherent(p, lo, f1, hi, f2);
+        else asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
         if (f1 == seq && f2 == seq) break;
         if (backoff > 0) __nanosleep(backoff);
     }
@@ -74,9 +89,10 @@ __device__ __forceinline__ void ll_flush(const LLView& v) {
     if (v.fence) __threadfence_system();
 }
 // one attempt (no spinning): many of these can be in flight before the first flag is inspected
-__device__ __forceinline__ bool ll_try_load(const uint4* p, unsigned int seq, double& out) {
+__device__ __forceinline__ bool ll_try_load(const uint4* p, unsigned int seq, double& out, int atomic_poll = 0) {
     unsigned int lo, f1, hi, f2;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+    if (atomic_poll) ll_read_coherent(p, lo, f1, hi, f2);
+    else asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
     out = __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
     return f1 == seq && f2 == seq;
 }
@@ -87,7 +103,7 @@ __device__ __forceinline__ void ll_push(const LLView& v, int64_t e, double val) 
 // sum over ranks of element e, in rank order (bit-identical on every rank)
 __device__ __forceinline__ double ll_sum(const LLView& v, int64_t e) {
     double s = 0.0;
-    for (int g = 0; g < v.nranks; ++g) s += ll_load(v.local + (size_t)g * v.cap + e, v.seq, v.backoff);
+    for (int g = 0; g < v.nranks; ++g) s += ll_load(v.local + (size_t)g * v.cap + e, v.seq, v.backoff, v.atomic_poll);
     return s;
 }
 // in-place all-reduce of a dense vector: one launch, every thread pushes its elements and then collects the peers' copies
@@ -104,7 +120,7 @@ __global__ void __launch_bounds__(256) ll_allgather_kernel(LLView v, const doubl
     ll_flush(v);
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < count * v.nranks; e += stride) {
         const int g = (int)(e / count);
-        dst[e] = ll_load(v.local + (size_t)g * v.cap + (e - (int64_t)g * count), v.seq, v.backoff);
+        dst[e] = ll_load(v.local + (size_t)g * v.cap + (e - (int64_t)g * count), v.seq, v.backoff, v.atomic_poll);
     }
 }
 
@@ -314,6 +330,8 @@ struct Comm {
         static const int fence = (getenv("DLRA_LL_FENCE") && atoi(getenv("DLRA_LL_FENCE")) != 0) ? 1 : 0;
         static const int backoff = getenv("DLRA_LL_BACKOFF_NS") ? atoi(getenv("DLRA_LL_BACKOFF_NS")) : 0;
         v.nranks = nranks; v.rank = rank; v.seq = sq; v.cap = ll_cap; v.fence = fence; v.backoff = backoff;
+        static const int atomic_poll = (getenv("DLRA_LL_ATOMIC_POLL") && atoi(getenv("DLRA_LL_ATOMIC_POLL")) != 0) ? 1 : 0;
+        v.atomic_poll = atomic_poll;
         v.local = (uint4*)(xbuf + base);
         for (int g = 0; g < P2P_MAX_RANKS; ++g) v.peer[g] = (uint4*)((xpeer[g] ? xpeer[g] : xbuf) + base);
         return v;

@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(TSQR_NW * 32, 1) tsqr_cta_kernel(int64_t rows,
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Two-level TSQR in ONE launch (8 <= nb <= 64 row blocks of 1024, i.e. up to 65536 rows per GPU — the headline shape).
+// Two-level TSQR in ONE launch (2 <= nb <= 64 row blocks of 1024, i.e. up to 65536 rows per GPU — the headline shape).
 // CTAs 0 .. nb-1 factor their panel (cta_panel_qr), publish R, and form their explicit Q block while CTA nb — which only waits
 // for the R factors — factors the stacked R's and forms the top Q; the panel CTAs then multiply their register-resident Q block by
 // their CP x CP block of the top Q and write the result once.  Against the three launches (level 0, level 1, apply_blocks) the
@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(32, 1) tsqr_xrank_kernel(P2PView v, LLView lv,
 #pragma unroll
                 for (int c = 0; c < CP; ++c) {
                     if (gr >= rows) a[q][c] = 0.0;
-                    else ok &= ll_try_load(lv.local + (size_t)g * lv.cap + i + c * CP, lv.seq, a[q][c]);
+                    else ok &= ll_try_load(lv.local + (size_t)g * lv.cap + i + c * CP, lv.seq, a[q][c], lv.atomic_poll);
                 }
                 if (!ok && lv.backoff > 0) __nanosleep(lv.backoff);
             } while (!ok);
@@ -904,9 +904,10 @@ inline double* tsqr_local(Ctx& cx, int64_t rows, int C, const double* A, int64_t
     double* Qtop = ws + nb * CP * CP;       // same shape
     double* rest = Qtop + nb * CP * CP;
     static const bool fused = !(getenv("DLRA_TSQR_FUSED") && atoi(getenv("DLRA_TSQR_FUSED")) == 0) && getenv("DLRA_TSQR_LEGACY") == nullptr;
-    // measured (profiles/r02/tsqr_fused_ab.txt): 64 blocks 87.5 -> 78.0 us; with 4 blocks (m = 4096) the single launch is SLOWER than the
-    // three small ones (68 vs 57 us), so short trees keep the three-launch path
-    static const int fused_min_nb = getenv("DLRA_TSQR_FUSED_MIN") ? atoi(getenv("DLRA_TSQR_FUSED_MIN")) : 8;
+    // measured (profiles/r02/tsqr_fused_ab.txt): 64 blocks 87.5 -> 77-81 us.  With 4 blocks (m = 4096) the single launch is slower than the
+    // three small ones in isolation (68 vs 57 us), but the m-side chain is not the critical one in the BUG step and three small launches beside
+    // the n-side kernel slow THAT one down (81.1 vs 76.7 us): BUG 1.114 -> 1.107 ms, KSL 1.507 -> 1.511 ms.  Default: every tree of 2..64 blocks.
+    static const int fused_min_nb = getenv("DLRA_TSQR_FUSED_MIN") ? atoi(getenv("DLRA_TSQR_FUSED_MIN")) : 2;
     if (fused && nb >= fused_min_nb && nb >= 2 && nb <= 64 && nb + 1 <= cx.num_sms / 2 && cx.sync != nullptr) {
         static unsigned long long attr_devs_f = 0;
         if (first_use_on_this_device(attr_devs_f)) {
