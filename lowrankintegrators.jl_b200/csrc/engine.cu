@@ -70,6 +70,7 @@ extern "C" int dlra_create(int device, int64_t n_local, int64_t m, int r0, int r
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_rnew, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_kqr, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_pass, cudaEventDisableTiming));
+        DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_lsum, cudaEventDisableTiming));
         DLRA_CUDA(cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming));
         const int64_t W = e->W;
         auto dmalloc = [&](int64_t doubles) {
@@ -149,6 +150,7 @@ extern "C" int dlra_destroy(dlra_handle h) {
     if (h->ev_rnew) cudaEventDestroy(h->ev_rnew);
     if (h->ev_kqr) cudaEventDestroy(h->ev_kqr);
     if (h->ev_pass) cudaEventDestroy(h->ev_pass);
+    if (h->ev_lsum) cudaEventDestroy(h->ev_lsum);
     if (h->ev_join2) cudaEventDestroy(h->ev_join2);
     h->UC.release();
     if (h->ev_ext) cudaEventDestroy(h->ev_ext);
@@ -446,6 +448,13 @@ static void join_aux(dlra_handle h) {
     DLRA_CUDA(cudaEventRecord(h->ev_join, h->ax.stream));
     DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->ev_join, 0));
 }
+// The pipelined BUG step leaves the sum of the next step's L partials running on the auxiliary stream; it writes VB.  A following BUG
+// step consumes it in stream order on that same stream; every other user of VB on the main stream must wait for it first.
+static void settle_aux(dlra_handle h) {
+    if (!h->lsum_pending) return;
+    DLRA_CUDA(cudaStreamWaitEvent(h->cx.stream, h->ev_lsum, 0));
+    h->lsum_pending = false;
+}
 static void ensure_qr_ws(Side sd, int64_t rows, int C) {
     const int cb = std::min(C, TSQR_MAXC);
     sd.tws->ensure(tsqr_ws_size(rows, cb, 8), sd.cx->stream);
@@ -547,6 +556,8 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
     const bool lsum_done = pre && h->kl_lsum_done;                  // ... whose L partials were already summed into VB
     h->kl_ready = false;
     h->kl_lsum_done = false;
+    if (lsum_done) h->lsum_pending = false;   // consumed on the auxiliary stream, in stream order behind the sum
+    else settle_aux(h);
     phase_mark(h, "step");
     // Single GPU: the whole L-side chain runs beside the K-side chain.  Row-sharded runs keep the cross-rank sum of L on the main
     // stream: measured at N = 2 (profiles/r02/multi_gpu_phases.txt) the spinning exchange kernel on the auxiliary stream competes
@@ -622,7 +633,9 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
                 DLRA_CUDA(cudaEventRecord(h->ev_pass, cx.stream));
                 DLRA_CUDA(cudaStreamWaitEvent(h->ax.stream, h->ev_pass, 0));
                 l_finalize(h, r, nparts, h->part.p, ldlp, 16, 1, nullptr, 0, nullptr, 0, r, h->V, m, &h->ax);
+                DLRA_CUDA(cudaEventRecord(h->ev_lsum, h->ax.stream));
                 h->kl_lsum_done = true;
+                h->lsum_pending = true;
             }
             if (m_aux) DLRA_CUDA(cudaStreamWaitEvent(cx.stream, h->ev_join2, 0));   // M is needed from here on
             h->gws.ensure(std::max(gemm_tn_ws(cx, n, r, r), gram_core_ws(n)), cx.stream);
@@ -682,6 +695,7 @@ static void bug_step(dlra_handle h, const StepCtx& sc) {
 // ---------------------------------------------------------------------------------------------------
 static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
     NvtxRange nvtx_step("dlra:ksl_primal_step");
+    settle_aux(h);
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;
@@ -712,6 +726,7 @@ static void ksl_primal_step(dlra_handle h, const StepCtx& sc) {
 
 static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
     NvtxRange nvtx_step("dlra:ksl_dual_step");
+    settle_aux(h);
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;
@@ -748,6 +763,7 @@ static void ksl_dual_step(dlra_handle h, const StepCtx& sc) {
 // ---------------------------------------------------------------------------------------------------
 static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rcap64, int* r_new_out, int* changed) {
     NvtxRange nvtx_step("dlra:rabug_step");
+    settle_aux(h);
     Ctx& cx = h->cx;
     const int r = h->r;
     const int r2 = 2 * r;
@@ -838,6 +854,7 @@ static void rabug_step(dlra_handle h, const StepCtx& sc, double tol, int64_t rca
 // ---------------------------------------------------------------------------------------------------
 static void greedy_step(dlra_handle h, const Delta& x) {
     NvtxRange nvtx_step("dlra:greedy_step");
+    settle_aux(h);
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;
@@ -874,6 +891,7 @@ static void ortho_complete(dlra_handle h, double* P, int r) {
 // ---------------------------------------------------------------------------------------------------
 static void greedy_two_factor_step(dlra_handle h, const Delta& x, int mode, bool carry_fsal, double t, double dt) {
     NvtxRange nvtx_step("dlra:greedy_two_factor_step");
+    settle_aux(h);
     Ctx& cx = h->cx;
     h->kl_ready = false;
     const int r = h->r;
@@ -1036,6 +1054,7 @@ extern "C" int dlra_truncated_svd(dlra_handle h, const double* A, int64_t ld, in
     DLRA_REQUIRE(A && ld >= h->n, "bad matrix pointer / leading dimension");
     DLRA_REQUIRE(r >= 0 && r <= h->rmax && oversample >= 0 && power_iters >= 0, "bad rank / oversampling / iteration count");
     DLRA_REQUIRE(r > 0 || tol >= 0.0, "either a rank or a tolerance is needed");
+    settle_aux(h);
     Ctx& cx = h->cx;
     const int64_t n = h->n, m = h->m;
     const int l = (int)std::min<int64_t>(std::min<int64_t>((r > 0 ? r : h->rmax) + oversample, 128), m);
@@ -1178,6 +1197,7 @@ __global__ void __launch_bounds__(256) pinv_from_svd_kernel(int r, const double*
 extern "C" int dlra_normal_component(dlra_handle h, const double* dY, int64_t ld, const double* C, int64_t ldc, double tol, double* out,
                                      int64_t ldo, double* fro_norm) {
     DLRA_API_BEGIN(h)
+    settle_aux(h);
     DLRA_REQUIRE(dY && ld >= h->n, "bad dY");
     DLRA_REQUIRE(!out || ldo >= h->n, "bad output leading dimension");
     DLRA_REQUIRE(!C || ldc >= h->r, "bad C leading dimension");

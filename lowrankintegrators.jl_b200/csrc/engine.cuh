@@ -111,7 +111,8 @@ struct dlra_engine {
     // software pipelining of the BUG step (pass_tri.cuh): ΔA·V0 already sits in UB and the per-CTA partials of ΔAᵀ·U0 in `part`
     bool kl_ready = false; int kl_nparts = 0; int64_t kl_ldlp = 0; int kl_rank = 0;
     bool kl_lsum_done = false;   // ... and the fixed-order sum of those partials already sits in VB (formed beside the core update)
-    cudaEvent_t ev_pass = nullptr;
+    cudaEvent_t ev_pass = nullptr, ev_lsum = nullptr;
+    bool lsum_pending = false;   // the early L sum may still be running on the auxiliary stream (it writes VB): see settle_aux
 
     // asynchronous factor snapshots (dlra_save_factors_async): two device staging slots, D2H on the copy stream
     dlra::DevBuf save_stage[2];

@@ -154,3 +154,26 @@ def test_truncated_svd_device(lri):
     Bd = torch.from_numpy(np.ascontiguousarray(B.T)).cuda().t()
     u = lri.truncated_svd_device(Bd, 5)
     assert rel_fro(u.full(), B) < 1e-13
+
+
+def test_switching_integrators_after_pipelined_bug_steps(lri):
+    # The pipelined BUG step leaves work for the NEXT step queued on the auxiliary stream (sum of the L partials into the spare V buffer,
+    # M = U1'U0 reading the old basis).  A different integrator that follows must see none of it: the KSL steps
+    # reuse those buffers on the main stream.  Shapes on the TMA fast path (lookahead on by default).
+    import torch
+    n, m, r = 4096, 512, 12
+    A = lowrank_stream(n, m, r, seed=11, eps=0.0)
+    snaps = [A(0.03 * k) for k in range(9)]
+    dsnaps = [torch.from_numpy(np.ascontiguousarray(s.T)).cuda().t() for s in snaps]
+    X0 = O.truncated_svd(snaps[0], r)
+    # (no greedy step in the sequence: the reference's greedy step does not advance `yprev`, so what follows it is not comparable)
+    galgs, oalgs = zip(*[_algs(lri)[k] for k in ("bug", "bug", "ksl_primal", "bug", "bug", "ksl_dual", "bug", "ksl_primal")])
+    oint = O.init(O.MatrixDataProblem(snaps, X0), oalgs[0], 1)
+    gint = lri.init(lri.MatrixDataProblem(dsnaps, lri.SVDLikeRepresentation(X0.U, X0.S, X0.V)), galgs[0], 1)
+    for k, (galg, oalg) in enumerate(zip(galgs, oalgs)):
+        O.step(oint, oalg)
+        lri.step(gint, galg)
+        gu, ou = gint.u, oint.u
+        assert rel_fro(gu.full(), ou.full()) <= TOL, (k, type(galg).__name__)
+        assert np.linalg.norm(gu.U.T @ gu.U - np.eye(gu.rank)) < 1e-12
+        assert np.linalg.norm(gu.V.T @ gu.V - np.eye(gu.rank)) < 1e-12
