@@ -165,6 +165,14 @@ extern "C" int dlra_destroy(dlra_handle h) {
 extern "C" int dlra_sync(dlra_handle h) {
     DLRA_API_BEGIN(h)
     DLRA_CUDA(cudaStreamSynchronize(h->cx.stream));
+    // the one-launch TSQR bounds its inter-CTA waits instead of hanging the device; a time-out (the CTAs of one launch were not
+    // co-resident for seconds: device shared with a foreign long-running kernel) must not pass silently
+    if (h->cx.sync) {
+        unsigned int w[12] = {0};   // cx.sync[0..3 of 8], ax.sync = cx.sync + 8
+        DLRA_CUDA(cudaMemcpy(w, h->cx.sync, sizeof(w), cudaMemcpyDeviceToHost));
+        if (w[2] != 0 || w[10] != 0)
+            throw CudaError(DLRA_ECUDA, "an inter-CTA wait of the one-launch TSQR timed out: factors computed since then are invalid");
+    }
     DLRA_API_END(h)
 }
 
