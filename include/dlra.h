@@ -190,6 +190,8 @@ int dlra_step_greedy(dlra_handle h, double t, double dt);
 enum { DLRA_GREEDY_DATA = 0, DLRA_GREEDY_HYBRID = 1 };
 int dlra_step_greedy_two_factor(dlra_handle h, int mode, int carry_fsal, double t, double dt);
 
+/* Blocks until everything enqueued on the engine's compute stream has run.  Steps are asynchronous: device-side failures surface
+ * here (DLRA_ECUDA), including a timed-out inter-CTA wait of the one-launch TSQR (factors computed since then are invalid). */
 int dlra_sync(dlra_handle h);
 /* The engine runs on its own (non-blocking) stream.  Device buffers handed to it must be complete: either synchronise the
  * producing stream on the host, or call this with that stream (a cudaStream_t; NULL = the legacy default stream) — the
